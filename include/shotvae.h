@@ -1,0 +1,213 @@
+/* libshotvae C ABI -- the drop-in boundary for the SHOT-VAE training-step hot path on B200 (sm_100a).
+ *
+ * The reference (FengHZ/SHOT-VAE) has no FFI of its own: its hot path sits behind a Python module
+ * API (shot_vae_model/vae.py:140-151, lib/criterion.py:32-57,97-108, lib/utils/mixup.py:5-41,
+ * main_shot_vae.py:281-366) and every FLOP is an ATen/cuDNN call.  This header is the boundary the
+ * Python shim (shot-vae_b200/shotvae_b200/_abi.py, ctypes) binds; each entry point names the
+ * reference call site(s) whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch allocates; the library never
+ *    allocates, frees or retains pointers past the call, except cached TMA descriptors);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *    synchronisation and is CUDA-graph capturable;
+ *  - activations are NHWC bf16 with the channel count padded to a multiple of 16; `NB = G * B`
+ *    images where G independent "pass groups" are batched and BatchNorm statistics are per group;
+ *  - return value 0 on success, negative on error (sv_last_error() gives the text, thread local).
+ *  - there is no CPU fallback anywhere.
+ */
+#ifndef SHOTVAE_H_
+#define SHOTVAE_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SV_ABI_VERSION 1
+#define SV_MAX_TAPS 16
+
+int sv_abi_version(void);
+const char* sv_last_error(void);
+/* 1 if the loaded library was built with the tcgen05/TMA implicit-GEMM path */
+int sv_has_tcgen05(void);
+/* number of kernel launches issued by this library since process start (bench `gpu_launches`) */
+long long sv_launch_count(void);
+
+/* ---- implicit GEMM (replaces every nn.Conv2d / nn.ConvTranspose2d fprop + dgrad call site:
+ *      wideresnet.py:12-14,29-35,41-43; preactresnet.py:31-36,56-59; decoder.py:13-58) ------------
+ * out[m, n] = sum_t sum_c A[gather(m, t), c] * Wt[t][n][c]   (+bias[n]) (+residual[m, n])
+ * rows m enumerate (nb, oh, ow) over NB x OH x OW; tap t reads input pixel
+ * (oh*in_stride + dy[t], ow*in_stride + dx[t]) (zero outside the image); the result is stored at
+ * output pixel (oh*out_stride + out_off_y, ow*out_stride + out_off_x) of an NB x OHf x OWf image.
+ * Per-channel sum / sum-of-squares of the stored values are atomically accumulated into
+ * stats[g][0][n], stats[g][1][n] (g = nb / group_images) for the following BatchNorm. */
+typedef struct {
+  const void* A;        /* bf16 [NB, H, W, C] */
+  const void* Wt;       /* bf16 [T][N][C] (packed by sv_pack_weight) */
+  void* out_bf16;       /* bf16 [NB, OHf, OWf, N] or NULL */
+  float* out_f32;       /* fp32 [NB, OHf, OWf, n_valid] or NULL */
+  const void* residual; /* bf16, layout of out_bf16, or NULL */
+  const float* bias;    /* fp32 [N] or NULL */
+  float* stats;         /* fp32 [G][2][N] (accumulated) or NULL */
+  int32_t NB, H, W, C;
+  int32_t OH, OW, N, T;
+  int32_t in_stride, out_stride, out_off_y, out_off_x;
+  int32_t OHf, OWf, n_valid, group_images;
+  int8_t dy[SV_MAX_TAPS];
+  int8_t dx[SV_MAX_TAPS];
+  int32_t impl;         /* 0 = auto, 1 = force mma.sync kernel, 2 = force tcgen05 kernel */
+} sv_igemm_args;
+int sv_igemm_fprop(const sv_igemm_args* a, void* stream);
+
+/* weight-gradient GEMM (replaces the cuDNN wgrad behind every conv / convT backward):
+ * part[s][n][t*C + c] = sum over the s-th slice of rows m of  Gr[m, n] * A[gather(m, t), c]
+ * Gr is dense bf16 [NB*OH*OW, N]; geometry fields as for sv_igemm_fprop.  `splits` slices of the
+ * row range are written to `partial` (fp32 [splits][N][T*C]); sv_wgrad_reduce sums them. */
+typedef struct {
+  const void* A;   /* bf16 [NB, H, W, C] */
+  const void* Gr;  /* bf16 [NB*OH*OW, N] */
+  float* partial;  /* fp32 [splits][N][T*C] */
+  int32_t NB, H, W, C;
+  int32_t OH, OW, N, T;
+  int32_t in_stride, splits;
+  int8_t dy[SV_MAX_TAPS];
+  int8_t dx[SV_MAX_TAPS];
+} sv_wgrad_args;
+int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream);
+/* grad[n*sn + c*sc + tap_index[t]*st] += sum_s partial[s][n][t*C + c]  for n < n_real, c < c_real */
+int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits, int32_t N, int32_t C, int32_t T,
+                    int32_t n_real, int32_t c_real, int64_t sn, int64_t sc, int64_t st,
+                    const int8_t* tap_index /* host, T entries */, void* stream);
+
+/* dst[t][n][c] (bf16) = src[n*sn + c*sc + tap_index[t]*st] for n < n_real, c < c_real else 0 */
+int sv_pack_weight(const float* src, void* dst, int32_t N, int32_t C, int32_t T, int32_t n_real, int32_t c_real,
+                   int64_t sn, int64_t sc, int64_t st, const int8_t* tap_index /* host */, void* stream);
+/* fp32 NCHW [NB, c_real, H, W] -> bf16 NHWC [NB, H, W, C] (zero padded channels) */
+int sv_pack_image(const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream);
+/* fp32 NHWC [NB, HW, c_real] -> fp32 NCHW [NB, c_real, HW] */
+int sv_nhwc_to_nchw_f32(const float* src, float* dst, int32_t NB, int32_t c_real, int32_t HW, void* stream);
+
+/* ---- BatchNorm2d (train mode) + LeakyReLU/ReLU (wideresnet.py:27-28,32-33,39-40,90-91;
+ *      preactresnet.py:29-30,33-34,54; decoder.py:19-20,...) -------------------------------------- */
+/* stats[G][2][C] (sum, sumsq over `count` values) -> mean, var(biased), scale=gamma*rstd,
+ * shift=beta-mean*scale, all [G][C] */
+int sv_bn_finalize(const float* stats, const float* gamma, const float* beta, float count, float eps, int32_t G,
+                   int32_t C, int32_t c_real, float* mean, float* var, float* scale, float* shift, void* stream);
+/* a = act(y*scale + shift), act = x>0 ? x : slope*x ; y, a bf16 [NB*HW, C] */
+int sv_bn_act_fwd(const void* y, void* a, const float* scale, const float* shift, float slope, int64_t rows_per_group,
+                  int32_t G, int32_t C, void* stream);
+/* feat[nb][c] = mean_hw act(y*scale+shift)   (transition BN + AdaptiveAvgPool2d, vae.py:107,142) */
+int sv_bn_act_gap_fwd(const void* y, float* feat, const float* scale, const float* shift, float slope, int32_t NB,
+                      int32_t HW, int32_t C, int32_t group_images, void* stream);
+/* dbeta[g][c] += sum g', dgamma[g][c] += sum g' * xhat, with g' = g_a * act'(y*scale+shift).
+ * g_a is bf16 [rows, C], or (g_feat != NULL) fp32 [NB][C] broadcast over HW and scaled by 1/HW. */
+int sv_bn_bwd_reduce(const void* g_a, const float* g_feat, const void* y, const float* scale, const float* shift,
+                     const float* mean, const float* var, float eps, float slope, int64_t rows_per_group, int32_t HW,
+                     int32_t G, int32_t C, float* dgamma, float* dbeta, void* stream);
+/* one term of the input gradient of BN+act */
+typedef struct {
+  const void* g_a;      /* bf16 [rows, C] or NULL when g_feat is used */
+  const float* g_feat;  /* fp32 [NB][C] or NULL */
+  const float* scale; const float* shift; const float* mean; const float* var;
+  const float* dgamma; const float* dbeta;    /* [G][C], from sv_bn_bwd_reduce */
+  float* grad_gamma; float* grad_beta;        /* parameter grads [c_real], accumulated (+=) */
+  float slope;
+  int32_t c_real;
+} sv_bn_bwd_term;
+/* g_y = [addend] + sum_terms scale*(g' - dbeta/M - xhat*dgamma/M)   (bf16 out) */
+int sv_bn_bwd_apply(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, const void* addend, void* g_y,
+                    float eps, int64_t rows_per_group, int32_t HW, int32_t G, int32_t C, void* stream);
+/* running_mean/var update in reference order for `npass` passes (momentum 0.1, unbiased var);
+ * mean/var are [npass][C] slices selected by the caller */
+int sv_bn_running_update(const float* const* mean_ptrs, const float* const* var_ptrs, int32_t npass, float count,
+                         float momentum, int32_t c_real, float* running_mean, float* running_var,
+                         int64_t* num_batches_tracked, void* stream);
+/* out[c] += sum_rows x[row][c]  (conv0 bias gradient) */
+int sv_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream);
+
+/* ---- small FP32 linears: the three inference heads (vae.py:10-15,143-145) and the k=1
+ *      ConvTranspose2d decoder stem (decoder.py:13-18) ------------------------------------------- */
+/* out[b][n] = sum_k x[b][k] * W(n,k) + bias[n];  W(n,k) = w_kn ? W[k*ldw + n] : W[n*ldw + k].
+ * x fp32 [B][ldx]; writes out_f32 [B][ldo] and/or out_bf16 [B][ldo]; optional stats[G][2][ldo]. */
+int sv_linear_fwd(const float* x, int32_t ldx, const float* W, int32_t ldw, int32_t w_kn, const float* bias,
+                  float* out_f32, void* out_bf16, int32_t ldo, float* stats, int32_t group_rows, int32_t B, int32_t N,
+                  int32_t K, void* stream);
+/* gx[b][k] (+)= sum_n g[b][n] * W(n,k); g fp32 or bf16 */
+int sv_linear_bwd_input(const float* g_f32, const void* g_bf16, int32_t ldg, const float* W, int32_t ldw, int32_t w_kn,
+                        float* gx, int32_t ldgx, int32_t accumulate, int32_t B, int32_t N, int32_t K, void* stream);
+/* dW(n,k) += sum_b g[b][n] * x[b][k]; dbias[n] += sum_b g[b][n] */
+int sv_linear_bwd_weight(const float* g_f32, const void* g_bf16, int32_t ldg, const float* x, int32_t ldx, float* dW,
+                         int32_t ldw, int32_t w_kn, float* dbias, int32_t B, int32_t N, int32_t K, void* stream);
+int sv_log_softmax_fwd(const float* logits, float* out, int32_t B, int32_t N, void* stream);
+/* g_logits = g_out - exp(out) * sum_n g_out */
+int sv_log_softmax_bwd(const float* g_out, const float* out, float* g_logits, int32_t B, int32_t N, void* stream);
+
+/* ---- Sample (vae.py:18-86): latent[b] = [ mu + exp(ls)*eps | y ] , ld = padded row length ---------
+ * mode 0: y = onehot(label)               (vae.py:47-49)
+ * mode 1: y = lam*onehot(label) + (1-lam)*onehot(label_mix), lam = *lam_dev, (1-lam) = lam_dev[1]
+ * mode 2: y = softmax((la + gumbel(u)) / temperature)  (vae.py:58-73) */
+int sv_sample_fwd(const float* mu, const float* ls, const float* la, const float* eps, const float* unif,
+                  const int64_t* label, const int64_t* label_mix, const float* lam_dev, int32_t mode,
+                  float temperature, int32_t B, int32_t D, int32_t nd, float* latent, int32_t ld, void* stream);
+/* g_mu (+)= g_z ; g_ls (+)= g_z*eps*exp(ls) ; mode 2: g_la (+)= softmax-backward(g_y)/temperature */
+int sv_sample_bwd(const float* g_latent, int32_t ld, const float* ls, const float* eps, const float* latent,
+                  int32_t mode, float temperature, int32_t B, int32_t D, int32_t nd, float* g_mu, float* g_ls,
+                  float* g_la, int32_t accumulate, void* stream);
+
+/* ---- VAECriterion (criterion.py:32-57), one fused loss + gradient pass --------------------------
+ * terms[0] = rec (BCE-with-logits sum / B, or MSE(sigmoid) sum / (2 B sigma^2)), terms[1] = KLc,
+ * terms[2] = KLd (all accumulated with atomics into a zeroed `terms`).
+ * x fp32 NCHW [B, ch, HW]; xhat fp32, NHWC [B, HW, ch] if xhat_nhwc else NCHW.
+ * g_xhat (optional): d rec / d xhat * (*g_scale or 1), written as bf16 NHWC [B, HW, g_ld] (zero
+ * padded) when g_bf16 != NULL and/or fp32 in xhat's layout when g_f32 != NULL. */
+int sv_elbo_rec_fwd_bwd(const float* x, const float* xhat, int32_t xhat_nhwc, int32_t B, int32_t ch, int32_t HW,
+                        int32_t bce, float x_sigma, const float* g_scale, float* terms, void* g_bf16, int32_t g_ld,
+                        float* g_f32, void* stream);
+int sv_elbo_kl_fwd(const float* mu, const float* ls, const float* la, int32_t B, int32_t D, int32_t nd, float* terms,
+                   void* stream);
+/* latent gradients of  w * ( kbc*|KLc - cmi| + kbd*|KLd - dmi| ) using terms[1], terms[2] from the
+ * forward; coef (device) = {w, kbc, cmi, kbd, dmi}.  unit != 0: instead write the plain
+ * d KLc/d mu, d KLc/d ls, d KLd/d la (the autograd path scales them itself). */
+int sv_elbo_kl_bwd(const float* mu, const float* ls, const float* la, const float* terms, const float* coef,
+                   int32_t unit, int32_t B, int32_t D, int32_t nd, float* g_mu, float* g_ls, float* g_la,
+                   int32_t accumulate, void* stream);
+
+/* ---- posterior-matching terms (main_shot_vae.py:316-321,358-361; ClsCriterion criterion.py:97-108)
+ * terms[0] += -(1/B) sum_b w_b sum_c la[b,c]*target[b,c];  terms[1] += (|mu-mu_t|^2 + |exp(ls)-sig_t|^2)/B
+ * target: dense fp32 [B][nd] (target != NULL) or lam*onehot(label_a) + (1-lam)*onehot(label_b).
+ * grads (optional): g_la (+)= -c_disc*target/B ; g_mu (+)= c_cont*2(mu-mu_t)/B ;
+ * g_ls (+)= c_cont*2(exp(ls)-sig_t)exp(ls)/B with c_disc = coef[0], c_cont = coef[1] (device). */
+int sv_posterior_fwd_bwd(const float* la, const float* target, const int64_t* label_a, const int64_t* label_b,
+                         const float* lam_dev, const float* mu, const float* ls, const float* mu_t, const float* sig_t,
+                         const float* coef, int32_t B, int32_t D, int32_t nd, float* terms, float* g_la, float* g_mu,
+                         float* g_ls, int32_t accumulate, void* stream);
+/* inference-KL monitor (main_shot_vae.py:331-339): *out += sum alpha*(la - log smooth_onehot(label))/B */
+int sv_inference_kl(const float* la, const int64_t* label, int32_t B, int32_t nd, float* out, void* stream);
+
+/* ---- mixup / label smoothing (mixup.py:5-41) ------------------------------------------------------
+ * lam_dev = {lam, 1-lam} (fp32, device).  image fp32 NCHW [B, img_elems]; writes the mixed image as
+ * fp32 NCHW (mixed_f32, optional) and as bf16 NHWC with `img_ld` channels (mixed_bf16, optional). */
+int sv_mixup_lerp(const float* image, const float* mu, const float* ls, const float* la, const int64_t* index,
+                  const float* lam_dev, int32_t B, int32_t ch, int32_t HW, int32_t D, int32_t nd, float* mixed_f32,
+                  void* mixed_bf16, int32_t img_ld, float* mixed_mu, float* mixed_sigma, float* mixed_alpha,
+                  void* stream);
+/* --om pairing (mixup.py:11-18, 93-99): index[i] = argmin_{2nd} KL(N_i || N_j), ties -> lower j.
+ * kl_out (optional) fp32 [B][B]. */
+int sv_pairwise_kl_second_nearest(const float* mu, const float* ls, int32_t B, int32_t D, int64_t* index,
+                                  float* kl_out, void* stream);
+
+/* ---- torch.optim.SGD step (main_shot_vae.py:198,365-366) over a flat FP32 arena -----------------
+ * g = grad*grad_scale + wd*p ; m = first ? g : mom*m + g ; p -= lr*m ; grad = 0.  hyper (device) =
+ * {lr, momentum, wd, grad_scale, first_step_flag}. */
+int sv_sgd_step(float* param, float* grad, float* momentum_buf, const float* hyper, int64_t n, void* stream);
+
+/* struct sizes, so the ctypes mirror can be checked at load time */
+int sv_sizeof_igemm_args(void);
+int sv_sizeof_wgrad_args(void);
+int sv_sizeof_bn_bwd_term(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHOTVAE_H_ */

@@ -1,0 +1,86 @@
+// C-ABI plumbing: error state, launch accounting, argument validation, kernel selection.
+#include <stdarg.h>
+#include <atomic>
+#include "common.cuh"
+#include "igemm.h"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void sv_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sv_check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    sv_set_error("%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return SV_ERR_CUDA;
+  }
+  return SV_OK;
+}
+
+extern "C" {
+
+int sv_abi_version(void) { return SV_ABI_VERSION; }
+const char* sv_last_error(void) { return g_err; }
+long long sv_launch_count(void) { return g_launches.load(); }
+int sv_sizeof_igemm_args(void) { return (int)sizeof(sv_igemm_args); }
+int sv_sizeof_wgrad_args(void) { return (int)sizeof(sv_wgrad_args); }
+int sv_sizeof_bn_bwd_term(void) { return (int)sizeof(sv_bn_bwd_term); }
+
+#ifdef SV_NO_TCGEN05
+int sv_has_tcgen05(void) { return 0; }
+#else
+int sv_has_tcgen05(void) { return 1; }
+#endif
+
+int sv_igemm_fprop(const sv_igemm_args* a, void* stream) {
+  SV_REQUIRE(a && a->A && a->Wt, "sv_igemm_fprop: null operand");
+  SV_REQUIRE(a->C % 16 == 0 && a->N % 16 == 0, "sv_igemm_fprop: C (%d) and N (%d) must be multiples of 16", a->C, a->N);
+  SV_REQUIRE(a->T >= 1 && a->T <= SV_MAX_TAPS, "sv_igemm_fprop: T=%d out of range", a->T);
+  SV_REQUIRE(a->NB > 0 && a->OH > 0 && a->OW > 0 && a->group_images > 0, "sv_igemm_fprop: bad geometry");
+  SV_REQUIRE(a->out_bf16 || a->out_f32, "sv_igemm_fprop: no output");
+  SV_REQUIRE((long long)a->NB * a->OH * a->OW < (1ll << 31), "sv_igemm_fprop: too many rows");
+  IgemmParams p;
+  p.A = (const bf16*)a->A; p.Wt = (const bf16*)a->Wt; p.out = (bf16*)a->out_bf16; p.outf = a->out_f32;
+  p.res = (const bf16*)a->residual; p.bias = a->bias; p.stats = a->stats;
+  p.NB = a->NB; p.H = a->H; p.W = a->W; p.C = a->C; p.OH = a->OH; p.OW = a->OW; p.N = a->N; p.T = a->T;
+  p.in_stride = a->in_stride; p.out_stride = a->out_stride; p.out_off_y = a->out_off_y; p.out_off_x = a->out_off_x;
+  p.OHf = a->OHf; p.OWf = a->OWf; p.n_valid = a->n_valid; p.group_images = a->group_images;
+  p.M = a->NB * a->OH * a->OW;
+  p.rows_per_group = a->group_images * a->OH * a->OW;
+  memcpy(p.dy, a->dy, SV_MAX_TAPS); memcpy(p.dx, a->dx, SV_MAX_TAPS);
+  cudaStream_t st = (cudaStream_t)stream;
+#ifndef SV_NO_TCGEN05
+  if (a->impl == 2) {
+    SV_REQUIRE(igemm_fprop_tc_supported(p), "sv_igemm_fprop: shape not supported by the tcgen05 kernel");
+    return igemm_fprop_tc(p, st);
+  }
+  if (a->impl == 0 && igemm_fprop_tc_supported(p)) return igemm_fprop_tc(p, st);
+#else
+  SV_REQUIRE(a->impl != 2, "sv_igemm_fprop: built without tcgen05");
+#endif
+  return igemm_fprop_mma(p, st);
+}
+
+int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream) {
+  SV_REQUIRE(a && a->A && a->Gr && a->partial, "sv_igemm_wgrad: null operand");
+  SV_REQUIRE(a->C % 8 == 0 && a->N % 16 == 0, "sv_igemm_wgrad: C (%d) %% 8, N (%d) %% 16", a->C, a->N);
+  SV_REQUIRE(a->T >= 1 && a->T <= SV_MAX_TAPS && a->splits >= 1, "sv_igemm_wgrad: bad T/splits");
+  WgradParams p;
+  p.A = (const bf16*)a->A; p.Gr = (const bf16*)a->Gr; p.partial = a->partial;
+  p.NB = a->NB; p.H = a->H; p.W = a->W; p.C = a->C; p.OH = a->OH; p.OW = a->OW; p.N = a->N; p.T = a->T;
+  p.in_stride = a->in_stride; p.splits = a->splits;
+  p.M = a->NB * a->OH * a->OW;
+  p.rows_per_split = ((p.M + a->splits - 1) / a->splits + 31) / 32 * 32;
+  memcpy(p.dy, a->dy, SV_MAX_TAPS); memcpy(p.dx, a->dx, SV_MAX_TAPS);
+  return igemm_wgrad_mma(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

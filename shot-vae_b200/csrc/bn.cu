@@ -1,0 +1,412 @@
+// BatchNorm (train mode) + LeakyReLU/ReLU forward/backward on NHWC bf16 tensors, per pass-group
+// statistics.  All kernels are HBM/L2-bandwidth bound: 16-byte vector accesses, a fixed channel
+// chunk per thread so the per-channel coefficients live in registers, shuffle-free register
+// accumulation with one shared-memory + one global atomic per (block, channel).
+#include "common.cuh"
+#include "../../include/shotvae.h"
+
+namespace {
+
+struct ColShape {
+  int cpr;      // 16-byte chunks per row (C/8)
+  int rl;       // row lanes per block
+  int threads;  // cpr*rl
+  int slabs;    // blocks per group
+  long long slab_rows;
+};
+
+static ColShape col_shape(long long rows_per_group, int G, int C) {
+  ColShape s;
+  s.cpr = C / 8;
+  s.rl = 256 / s.cpr;
+  if (s.rl < 1) s.rl = 1;
+  s.threads = s.cpr * s.rl;
+  long long want = (148ll * 8) / (G > 0 ? G : 1);
+  if (want < 1) want = 1;
+  long long by_rows = ceil_div_ll(rows_per_group, (long long)s.rl * 4);
+  s.slabs = (int)(by_rows < want ? by_rows : want);
+  if (s.slabs < 1) s.slabs = 1;
+  s.slab_rows = ceil_div_ll(rows_per_group, s.slabs);
+  return s;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float count, float eps, int G, int C, int c_real,
+                                   float* mean, float* var, float* scale, float* shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * C) return;
+  const int g = i / C, c = i - g * C;
+  float m = 0.f, v = 0.f, sc = 0.f, sh = 0.f;
+  if (c < c_real) {
+    const double s1 = stats[(size_t)(g * 2 + 0) * C + c], s2 = stats[(size_t)(g * 2 + 1) * C + c];
+    const double dm = s1 / count;
+    double dv = s2 / count - dm * dm;
+    if (dv < 0.0) dv = 0.0;
+    m = (float)dm;
+    v = (float)dv;
+    const float rstd = rsqrtf(v + eps);
+    sc = gamma[c] * rstd;
+    sh = beta[c] - m * sc;
+  }
+  mean[i] = m; var[i] = v; scale[i] = sc; shift[i] = sh;
+}
+
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict__ y, bf16* __restrict__ a,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         float slope, long long rows_per_group, long long slab_rows, int C) {
+  const int cpr = C / 8;
+  const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
+  const int g = blockIdx.y;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[(size_t)g * C + chunk * 8 + j];
+    sh[j] = shift[(size_t)g * C + chunk * 8 + j];
+  }
+  const long long r0 = (long long)blockIdx.x * slab_rows;
+  const long long r1 = min(r0 + slab_rows, rows_per_group);
+  for (long long r = r0 + rl; r < r1; r += nrl) {
+    const size_t off = ((size_t)g * rows_per_group + r) * C + chunk * 8;
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + off), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = fmaf(v[j], sc[j], sh[j]);
+      v[j] = t > 0.f ? t : slope * t;
+    }
+    *reinterpret_cast<bf16x8*>(a + off) = pack8(v);
+  }
+}
+
+__global__ void bn_act_gap_kernel(const bf16* __restrict__ y, float* __restrict__ feat, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, float slope, int NB, int HW, int C, int group_images) {
+  const int cpr = C / 8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)NB * cpr) return;
+  const int nb = (int)(i / cpr), chunk = (int)(i % cpr);
+  const int g = nb / group_images;
+  float sc[8], sh[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[(size_t)g * C + chunk * 8 + j];
+    sh[j] = shift[(size_t)g * C + chunk * 8 + j];
+    acc[j] = 0.f;
+  }
+  for (int p = 0; p < HW; ++p) {
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + ((size_t)nb * HW + p) * C + chunk * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = fmaf(v[j], sc[j], sh[j]);
+      acc[j] += t > 0.f ? t : slope * t;
+    }
+  }
+  const float inv = 1.f / (float)HW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) feat[(size_t)nb * C + chunk * 8 + j] = acc[j] * inv;
+}
+
+// dgamma/dbeta reduction
+template <bool FEAT>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ g_a, const float* __restrict__ g_feat,
+                                                            const bf16* __restrict__ y, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, const float* __restrict__ mean,
+                                                            const float* __restrict__ var, float eps, float slope,
+                                                            long long rows_per_group, long long slab_rows, int HW, int C,
+                                                            float* dgamma, float* dbeta) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int cpr = C / 8;
+  const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
+  const int g = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  float sc[8], sh[8], mu[8], rs[8], ab[8], ag[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const size_t k = (size_t)g * C + chunk * 8 + j;
+    sc[j] = scale[k]; sh[j] = shift[k]; mu[j] = mean[k]; rs[j] = rsqrtf(var[k] + eps);
+    ab[j] = 0.f; ag[j] = 0.f;
+  }
+  const float inv_hw = 1.f / (float)HW;
+  const long long r0 = (long long)blockIdx.x * slab_rows;
+  const long long r1 = min(r0 + slab_rows, rows_per_group);
+  for (long long r = r0 + rl; r < r1; r += nrl) {
+    const size_t row = (size_t)g * rows_per_group + r;
+    const size_t off = row * C + chunk * 8;
+    float gv[8], yv[8];
+    if (FEAT) {
+      const size_t nb = row / HW;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = g_feat[nb * C + chunk * 8 + j] * inv_hw;
+    } else {
+      unpack8(*reinterpret_cast<const bf16x8*>(g_a + off), gv);
+    }
+    unpack8(*reinterpret_cast<const bf16x8*>(y + off), yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float pre = fmaf(yv[j], sc[j], sh[j]);
+      const float gp = pre > 0.f ? gv[j] : slope * gv[j];
+      ab[j] += gp;
+      ag[j] += gp * (yv[j] - mu[j]) * rs[j];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_acc[chunk * 8 + j], ag[j]);
+    atomicAdd(&s_acc[C + chunk * 8 + j], ab[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&dgamma[(size_t)g * C + i], s_acc[i]);
+    atomicAdd(&dbeta[(size_t)g * C + i], s_acc[C + i]);
+  }
+}
+
+struct BwdTerms {
+  sv_bn_bwd_term t[2];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdTerms T, const bf16* __restrict__ y,
+                                                           const bf16* __restrict__ addend, bf16* __restrict__ g_y, float eps,
+                                                           long long rows_per_group, long long slab_rows, int HW, int G, int C) {
+  const int cpr = C / 8;
+  const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
+  const int g = blockIdx.y;
+  const float invM = 1.f / (float)rows_per_group;
+  float sc[2][8], sh[2][8], k1[2][8], k0[2][8];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    if (t < T.n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const size_t k = (size_t)g * C + chunk * 8 + j;
+        const float s = T.t[t].scale[k], rstd = rsqrtf(T.t[t].var[k] + eps);
+        sc[t][j] = s;
+        sh[t][j] = T.t[t].shift[k];
+        k1[t][j] = -s * rstd * T.t[t].dgamma[k] * invM;
+        k0[t][j] = -s * T.t[t].dbeta[k] * invM - k1[t][j] * T.t[t].mean[k];
+      }
+      // parameter gradients: one block adds sum_g dgamma / dbeta
+      if (blockIdx.x == 0 && blockIdx.y == 0 && rl == 0 && T.t[t].grad_gamma != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = chunk * 8 + j;
+          if (c < T.t[t].c_real) {
+            float sg = 0.f, sb = 0.f;
+            for (int gg = 0; gg < G; ++gg) {
+              sg += T.t[t].dgamma[(size_t)gg * C + c];
+              sb += T.t[t].dbeta[(size_t)gg * C + c];
+            }
+            T.t[t].grad_gamma[c] += sg;
+            T.t[t].grad_beta[c] += sb;
+          }
+        }
+      }
+    }
+  }
+  const float inv_hw = 1.f / (float)HW;
+  const long long r0 = (long long)blockIdx.x * slab_rows;
+  const long long r1 = min(r0 + slab_rows, rows_per_group);
+  for (long long r = r0 + rl; r < r1; r += nrl) {
+    const size_t row = (size_t)g * rows_per_group + r;
+    const size_t off = row * C + chunk * 8;
+    float yv[8], o[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + off), yv);
+    if (addend != nullptr) {
+      unpack8(*reinterpret_cast<const bf16x8*>(addend + off), o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (t < T.n) {
+        float gv[8];
+        if (T.t[t].g_feat != nullptr) {
+          const size_t nb = row / HW;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gv[j] = T.t[t].g_feat[nb * C + chunk * 8 + j] * inv_hw;
+        } else {
+          unpack8(*reinterpret_cast<const bf16x8*>((const bf16*)T.t[t].g_a + off), gv);
+        }
+        const float slope = T.t[t].slope;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pre = fmaf(yv[j], sc[t][j], sh[t][j]);
+          const float gp = pre > 0.f ? gv[j] : slope * gv[j];
+          o[j] += sc[t][j] * gp + k1[t][j] * yv[j] + k0[t][j];
+        }
+      }
+    }
+    *reinterpret_cast<bf16x8*>(g_y + off) = pack8(o);
+  }
+}
+
+struct PassPtrs {
+  const float* mean[8];
+  const float* var[8];
+};
+
+__global__ void bn_running_update_kernel(PassPtrs P, int npass, float count, float momentum, int c_real,
+                                         float* running_mean, float* running_var, long long* nbt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt != nullptr) *nbt += npass;
+  if (c >= c_real) return;
+  float rm = running_mean[c], rv = running_var[c];
+  const float unbias = count > 1.f ? count / (count - 1.f) : 1.f;
+  for (int p = 0; p < npass; ++p) {
+    rm = (1.f - momentum) * rm + momentum * P.mean[p][c];
+    rv = (1.f - momentum) * rv + momentum * (P.var[p][c] * unbias);
+  }
+  running_mean[c] = rm;
+  running_var[c] = rv;
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long rows,
+                                                     long long slab_rows, int C, int c_real) {
+  extern __shared__ float s_acc[];  // [C]
+  const int cpr = C / 8;
+  const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  const long long r0 = (long long)blockIdx.x * slab_rows;
+  const long long r1 = min(r0 + slab_rows, rows);
+  for (long long r = r0 + rl; r < r1; r += nrl) {
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + (size_t)r * C + chunk * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += v[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[chunk * 8 + j], a[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < c_real; i += blockDim.x) atomicAdd(&out[i], s_acc[i]);
+}
+
+__global__ void pack_image_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long npix, int c_real, int HW,
+                                  int C) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const long long nb = i / HW, p = i - nb * HW;
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      v[j] = c < c_real ? src[((size_t)nb * c_real + c) * HW + p] : 0.f;
+    }
+    *reinterpret_cast<bf16x8*>(dst + (size_t)i * C + c0) = pack8(v);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, long long total, int c_real,
+                                    int HW) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long p = i % HW;
+  const long long r = i / HW;
+  const int c = (int)(r % c_real);
+  const long long nb = r / c_real;
+  dst[i] = src[((size_t)nb * HW + p) * c_real + c];
+}
+
+}  // namespace
+
+extern "C" {
+
+int sv_bn_finalize(const float* stats, const float* gamma, const float* beta, float count, float eps, int32_t G, int32_t C,
+                   int32_t c_real, float* mean, float* var, float* scale, float* shift, void* stream) {
+  SV_REQUIRE(stats && gamma && beta && mean && var && scale && shift, "sv_bn_finalize: null pointer");
+  const int n = G * C;
+  bn_finalize_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(stats, gamma, beta, count, eps, G, C, c_real, mean,
+                                                                        var, scale, shift);
+  return sv_check_launch("bn_finalize");
+}
+
+int sv_bn_act_fwd(const void* y, void* a, const float* scale, const float* shift, float slope, int64_t rows_per_group,
+                  int32_t G, int32_t C, void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_act_fwd: unsupported C=%d", C);
+  const ColShape s = col_shape(rows_per_group, G, C);
+  bn_act_fwd_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, scale, shift, slope,
+                                                                              rows_per_group, s.slab_rows, C);
+  return sv_check_launch("bn_act_fwd");
+}
+
+int sv_bn_act_gap_fwd(const void* y, float* feat, const float* scale, const float* shift, float slope, int32_t NB, int32_t HW,
+                      int32_t C, int32_t group_images, void* stream) {
+  SV_REQUIRE(C % 8 == 0, "sv_bn_act_gap_fwd: C %% 8");
+  const long long n = (long long)NB * (C / 8);
+  bn_act_gap_kernel<<<(int)ceil_div_ll(n, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)y, feat, scale, shift, slope, NB,
+                                                                               HW, C, group_images);
+  return sv_check_launch("bn_act_gap");
+}
+
+int sv_bn_bwd_reduce(const void* g_a, const float* g_feat, const void* y, const float* scale, const float* shift,
+                     const float* mean, const float* var, float eps, float slope, int64_t rows_per_group, int32_t HW,
+                     int32_t G, int32_t C, float* dgamma, float* dbeta, void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_bwd_reduce: unsupported C=%d", C);
+  SV_REQUIRE((g_a != nullptr) != (g_feat != nullptr), "sv_bn_bwd_reduce: exactly one of g_a / g_feat");
+  const ColShape s = col_shape(rows_per_group, G, C);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  if (g_feat)
+    bn_bwd_reduce_kernel<true><<<dim3(s.slabs, G), s.threads, smem, (cudaStream_t)stream>>>(
+        nullptr, g_feat, (const bf16*)y, scale, shift, mean, var, eps, slope, rows_per_group, s.slab_rows, HW, C, dgamma, dbeta);
+  else
+    bn_bwd_reduce_kernel<false><<<dim3(s.slabs, G), s.threads, smem, (cudaStream_t)stream>>>(
+        (const bf16*)g_a, nullptr, (const bf16*)y, scale, shift, mean, var, eps, slope, rows_per_group, s.slab_rows, HW, C,
+        dgamma, dbeta);
+  return sv_check_launch("bn_bwd_reduce");
+}
+
+int sv_bn_bwd_apply(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, const void* addend, void* g_y, float eps,
+                    int64_t rows_per_group, int32_t HW, int32_t G, int32_t C, void* stream) {
+  SV_REQUIRE(nterms >= 1 && nterms <= 2, "sv_bn_bwd_apply: nterms must be 1 or 2");
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_bwd_apply: unsupported C=%d", C);
+  BwdTerms T;
+  memset(&T, 0, sizeof(T));
+  T.n = nterms;
+  for (int i = 0; i < nterms; ++i) T.t[i] = terms[i];
+  const ColShape s = col_shape(rows_per_group, G, C);
+  bn_bwd_apply_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(T, (const bf16*)y, (const bf16*)addend,
+                                                                                (bf16*)g_y, eps, rows_per_group, s.slab_rows,
+                                                                                HW, G, C);
+  return sv_check_launch("bn_bwd_apply");
+}
+
+int sv_bn_running_update(const float* const* mean_ptrs, const float* const* var_ptrs, int32_t npass, float count,
+                         float momentum, int32_t c_real, float* running_mean, float* running_var,
+                         int64_t* num_batches_tracked, void* stream) {
+  SV_REQUIRE(npass >= 1 && npass <= 8, "sv_bn_running_update: npass out of range");
+  PassPtrs P;
+  for (int i = 0; i < npass; ++i) { P.mean[i] = mean_ptrs[i]; P.var[i] = var_ptrs[i]; }
+  bn_running_update_kernel<<<ceil_div(c_real, 128), 128, 0, (cudaStream_t)stream>>>(
+      P, npass, count, momentum, c_real, running_mean, running_var, (long long*)num_batches_tracked);
+  return sv_check_launch("bn_running_update");
+}
+
+int sv_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_colsum_bf16: unsupported C=%d", C);
+  const ColShape s = col_shape(rows, 1, C);
+  colsum_kernel<<<s.slabs, s.threads, (size_t)C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, out, rows,
+                                                                                         s.slab_rows, C, c_real);
+  return sv_check_launch("colsum");
+}
+
+int sv_pack_image(const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream) {
+  SV_REQUIRE(C % 8 == 0, "sv_pack_image: C %% 8");
+  const long long npix = (long long)NB * HW;
+  pack_image_kernel<<<(int)ceil_div_ll(npix, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, npix, c_real, HW, C);
+  return sv_check_launch("pack_image");
+}
+
+int sv_nhwc_to_nchw_f32(const float* src, float* dst, int32_t NB, int32_t c_real, int32_t HW, void* stream) {
+  const long long total = (long long)NB * c_real * HW;
+  nhwc_to_nchw_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, total, c_real, HW);
+  return sv_check_launch("nhwc_to_nchw");
+}
+
+}  // extern "C"

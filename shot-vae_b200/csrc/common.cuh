@@ -1,0 +1,86 @@
+// Shared device/host helpers for libshotvae (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define SV_OK 0
+#define SV_ERR_ARG (-1)
+#define SV_ERR_CUDA (-2)
+#define SV_ERR_UNSUPPORTED (-3)
+
+void sv_set_error(const char* fmt, ...);
+int sv_check_launch(const char* what);
+
+#define SV_REQUIRE(cond, ...)                                                                     \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      sv_set_error(__VA_ARGS__);                                                                  \
+      return SV_ERR_ARG;                                                                          \
+    }                                                                                             \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+struct __align__(16) bf16x8 {
+  bf162 v[4];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in thread 0 (and broadcast through smem to all threads).
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* red /* >= NT/32 floats */) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = (l < NT / 32) ? red[l] : 0.f;
+    r = warp_sum(r);
+    if (l == 0) red[0] = r;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

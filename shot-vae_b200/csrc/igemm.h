@@ -1,0 +1,40 @@
+// Internal parameter blocks shared by the implicit-GEMM kernels (mma.sync and tcgen05 paths).
+#pragma once
+#include "common.cuh"
+#include "../../include/shotvae.h"
+
+struct IgemmParams {
+  const bf16* A;
+  const bf16* Wt;
+  bf16* out;
+  float* outf;
+  const bf16* res;
+  const float* bias;
+  float* stats;
+  int NB, H, W, C;
+  int OH, OW, N, T;
+  int in_stride, out_stride, out_off_y, out_off_x;
+  int OHf, OWf, n_valid, group_images;
+  int M;               // NB*OH*OW
+  int rows_per_group;  // group_images*OH*OW
+  int8_t dy[SV_MAX_TAPS];
+  int8_t dx[SV_MAX_TAPS];
+};
+
+struct WgradParams {
+  const bf16* A;
+  const bf16* Gr;
+  float* partial;
+  int NB, H, W, C;
+  int OH, OW, N, T;
+  int in_stride, splits;
+  int M, rows_per_split;
+  int8_t dy[SV_MAX_TAPS];
+  int8_t dx[SV_MAX_TAPS];
+};
+
+int igemm_fprop_mma(const IgemmParams& p, cudaStream_t st);
+int igemm_wgrad_mma(const WgradParams& p, cudaStream_t st);
+// tcgen05 + TMA path (igemm_tc.cu). Returns SV_ERR_UNSUPPORTED when the shape is not covered.
+bool igemm_fprop_tc_supported(const IgemmParams& p);
+int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st);

@@ -1,0 +1,567 @@
+"""Network plan + executor: the sequence of libshotvae kernels that realises the VAE forward /
+backward passes of the SHOT-VAE hot path (reference shot_vae_model/{wideresnet,preactresnet,decoder,vae}.py).
+
+Design:
+  * parameters live in ONE flat FP32 arena (reference state_dict layouts: Conv OIHW, ConvT IOHW, BN
+    weight/bias, Linear [out,in]); gradients and SGD momentum are sibling arenas.  nn.Parameters of the
+    drop-in modules are views into it, the data-parallel all-reduce and the fused SGD run on the flat
+    buffers.
+  * activations are NHWC bf16; `G` independent passes (each with its own BatchNorm statistics) are
+    batched into one launch sequence (NB = G*B images).
+  * every conv / convT is an implicit GEMM described by a tap table (sv_igemm_fprop / sv_igemm_wgrad);
+    stride-2 input gradients and transposed convolutions are decomposed into output-parity phases.
+"""
+import ctypes as C
+import math
+import re
+from collections import OrderedDict
+
+import torch
+
+from . import _abi
+from ._abi import lib, check, ptr, IgemmArgs, WgradArgs, BnBwdTerm, taps_array
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+WG_WORKSPACE_FLOATS = 24 * 1024 * 1024
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+# ------------------------------------------------------------------------------------ topology
+class Unit:
+    def __init__(self, prefix, cin, cout, stride, shortcut):
+        self.prefix, self.cin, self.cout, self.stride, self.shortcut = prefix, cin, cout, stride, shortcut
+
+
+def encoder_topology(name):
+    """Unit list of the supported encoders (wideresnet.py:68-99, preactresnet.py:85-117)."""
+    if "wideresnet" in name:
+        nums = re.findall(r"\d+", name)
+        depth, width = int(nums[0]), int(nums[1])
+        if (depth - 4) % 6 != 0:
+            raise AssertionError("depth should be 6n+4")
+        n_unit = (depth - 4) // 6
+        units, cin = [], 16
+        for bi, base in enumerate((16, 32, 64)):
+            cout = int(base * width)
+            for ui in range(n_unit):
+                stride = 2 if (bi > 0 and ui == 0) else 1
+                c_in = cin if ui == 0 else cout
+                units.append(Unit("feature_extractor.encoder.wideblock%d.wide_block.wideunit%d" % (bi + 1, ui + 1),
+                                  c_in, cout, stride, c_in != cout or stride != 1))
+            cin = cout
+        return dict(f0=16, units=units, slope=0.01, shortcut_slope=0.01, feat=cin)
+    if name == "preactresnet18":
+        units, cin = [], 64
+        for bi, cout in enumerate((64, 128, 256, 512)):
+            for ui in range(2):
+                stride = 2 if (bi > 0 and ui == 0) else 1
+                c_in = cin if ui == 0 else cout
+                units.append(Unit("feature_extractor.encoder.block%d.preact_block.unit%d" % (bi + 1, ui + 1),
+                                  c_in, cout, stride, c_in != cout or stride != 1))
+            cin = cout
+        # the PreAct shortcut is BN -> conv1x1 with NO activation: slope 1.0 makes act() the identity
+        return dict(f0=64, units=units, slope=0.0, shortcut_slope=1.0, feat=512)
+    raise NotImplementedError("{} not implemented".format(name))
+
+
+DEC_CHANNELS = (1024, 512, 256, 128, 64)
+
+
+def conv_taps(k, pad):
+    return [(ky * k + kx, ky - pad, kx - pad) for ky in range(k) for kx in range(k)]
+
+
+def dgrad_phase_taps(k, s, pad):
+    """Input-gradient of a (k, stride s, pad) convolution == forward of the transposed convolution,
+    split by output parity: {(py, px): [(tap_index, off_y, off_x)]}; out[s*j+py] += in[j+off] * w[tap]."""
+    res = {}
+    for py in range(s):
+        for px in range(s):
+            taps = []
+            for ky in range(k):
+                if (py + pad - ky) % s:
+                    continue
+                for kx in range(k):
+                    if (px + pad - kx) % s:
+                        continue
+                    taps.append((ky * k + kx, (py + pad - ky) // s, (px + pad - kx) // s))
+            res[(py, px)] = taps
+    return res
+
+
+def live_taps(taps, OH, OW, H, W, in_stride):
+    """Drops taps that read outside the image for every output position (e.g. 12 of the 16 taps of the
+    1x1 -> 2x2 decoder layer)."""
+    def any_in(n_out, n_in, d):
+        return any(0 <= o * in_stride + d < n_in for o in range(n_out))
+    return [t for t in taps if any_in(OH, H, t[1]) and any_in(OW, W, t[2])]
+
+
+# ------------------------------------------------------------------------------------ context
+class Ctx:
+    """Per-pass buffers (activations saved for backward, BN statistics, gradients).  Buffers are
+    allocated on first use and then reused, so every later pass replays the same addresses
+    (CUDA-graph capturable)."""
+
+    def __init__(self, net, G, B):
+        self.net, self.G, self.B, self.NB = net, G, B, G * B
+        self.dev = net.device
+        self.bufs = {}
+        self.args = {}
+        self.zero_arena = torch.zeros(3 * 1024 * 1024, dtype=torch.float32, device=self.dev)
+        self.zero_used = 0
+        self.bn = OrderedDict()   # bn name -> dict(mean, var, count, ...)
+        self.tape = []
+
+    def t(self, name, shape, dtype=torch.bfloat16):
+        b = self.bufs.get(name)
+        if b is None:
+            b = torch.empty(shape, dtype=dtype, device=self.dev)
+            self.bufs[name] = b
+        return b
+
+    def z(self, name, numel):
+        """fp32 buffer that is zero at the start of every pass (one memset for all of them)."""
+        b = self.bufs.get(name)
+        if b is None:
+            n = (numel + 3) // 4 * 4
+            assert self.zero_used + n <= self.zero_arena.numel(), "zero arena exhausted"
+            b = self.zero_arena[self.zero_used:self.zero_used + numel]
+            self.zero_used += n
+            self.bufs[name] = b
+        return b
+
+    def reset(self):
+        if self.zero_used:
+            self.zero_arena[:self.zero_used].zero_()
+        else:
+            self.zero_arena.zero_()
+
+
+# ------------------------------------------------------------------------------------ the net
+class Net:
+    def __init__(self, encoder_name, nd, ldc, in_ch, named_params, named_buffers, device, temperature=0.67, impl=0):
+        self.encoder_name, self.nd, self.ldc, self.in_ch = encoder_name, nd, ldc, in_ch
+        self.device = torch.device(device)
+        self.topo = encoder_topology(encoder_name)
+        self.temperature = float(temperature)
+        self.impl = impl
+        self.latent = ldc + nd
+        # ---- flat arenas
+        self.pnames = list(named_params.keys())
+        self.poff, off = {}, 0
+        for k, v in named_params.items():
+            self.poff[k] = (off, v.numel(), tuple(v.shape))
+            off += v.numel()
+        self.n_params = off
+        n_alloc = (off + 3) // 4 * 4
+        self.params = torch.zeros(n_alloc, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(n_alloc, dtype=torch.float32, device=self.device)
+        self.momentum = torch.zeros(n_alloc, dtype=torch.float32, device=self.device)
+        for k, v in named_params.items():
+            self.p(k).copy_(v.detach().to(self.device, torch.float32))
+        self.boff, off = {}, 0
+        for k, v in named_buffers.items():
+            if v.dtype == torch.float32:
+                self.boff[k] = (off, v.numel())
+                off += v.numel()
+        self.running = torch.zeros(max(off, 1), dtype=torch.float32, device=self.device)
+        self.nbt_names = [k for k, v in named_buffers.items() if v.dtype != torch.float32]
+        self.nbt = torch.zeros(max(len(self.nbt_names), 1), dtype=torch.int64, device=self.device)
+        for k, v in named_buffers.items():
+            self.b(k).copy_(v.detach().to(self.device))
+        self.wg_ws = torch.empty(WG_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
+        self._build_packs()
+
+    # ---- views
+    def p(self, name):
+        o, n, shp = self.poff[name]
+        return self.params[o:o + n].view(shp)
+
+    def g(self, name):
+        o, n, shp = self.poff[name]
+        return self.grads[o:o + n].view(shp)
+
+    def b(self, name):
+        if name in self.boff:
+            o, n = self.boff[name]
+            return self.running[o:o + n]
+        i = self.nbt_names.index(name)
+        return self.nbt[i:i + 1].view(())
+
+    # ---- weight packing recipes ------------------------------------------------------------
+    def _add_pack(self, key, wname, N, C, taps, n_real, c_real, sn, sc, st):
+        T = len(taps)
+        dst = torch.zeros(T, N, C, dtype=torch.bfloat16, device=self.device)
+        self.packs[key] = dict(w=dst, taps=taps, wname=wname, N=N, C=C, T=T, n_real=n_real, c_real=c_real,
+                               sn=sn, sc=sc, st=st, tidx=taps_array([t[0] for t in taps]))
+
+    def _build_packs(self):
+        self.packs = OrderedDict()
+        topo = self.topo
+        f0 = topo["f0"]
+        cin_p = pad16(self.in_ch)
+        # conv0: Conv2d(in_ch, f0, 3, 1, 1, bias) -- OIHW
+        self._add_pack("conv0.f", "feature_extractor.encoder.pre_process.conv0.weight", f0, cin_p, conv_taps(3, 1),
+                       f0, self.in_ch, self.in_ch * 9, 9, 1)
+        H = 32
+        for ui, u in enumerate(topo["units"]):
+            Ho = H // u.stride
+            for cname, ci, co, k, s, pad, hin in (("conv1", u.cin, u.cout, 3, u.stride, 1, H),
+                                                 ("conv2", u.cout, u.cout, 3, 1, 1, Ho),
+                                                 ("sc", u.cin, u.cout, 1, u.stride, 0, H)):
+                if cname == "sc" and not u.shortcut:
+                    continue
+                wname = u.prefix + (".i_block.conv.weight" if cname == "sc" else ".f_block.%s.weight" % cname)
+                K = k * k
+                hout = hin // s
+                self._add_pack("u%d.%s.f" % (ui, cname), wname, co, ci, conv_taps(k, pad), co, ci, ci * K, K, 1)
+                for (py, px), taps in dgrad_phase_taps(k, s, pad).items():
+                    taps = live_taps(taps, hout, hout, hout, hout, 1)
+                    if taps:
+                        self._add_pack("u%d.%s.d%d%d" % (ui, cname, py, px), wname, ci, co, taps, ci, co, K, ci * K, 1)
+            H = Ho
+        # decoder: ConvTranspose2d weights are [Cin, Cout, k, k]
+        cin, hin = DEC_CHANNELS[0], 1
+        for li, cout in enumerate(DEC_CHANNELS[1:] + (self.in_ch,)):
+            wname = "feature_reconstructor.decoder.%d.weight" % (3 * (li + 1))
+            cout_p = pad16(cout)
+            for (py, px), taps in dgrad_phase_taps(4, 2, 1).items():
+                taps = live_taps(taps, hin, hin, hin, hin, 1)
+                self._add_pack("d%d.f%d%d" % (li + 1, py, px), wname, cout_p, cin, taps, cout, cin, 16, cout * 16, 1)
+            taps = live_taps(conv_taps(4, 1), hin, hin, 2 * hin, 2 * hin, 2)
+            self._add_pack("d%d.d" % (li + 1), wname, cin, cout_p, taps, cin, cout, cout * 16, 16, 1)
+            cin, hin = cout, hin * 2
+
+    def pack_weights(self):
+        """FP32 master weights -> bf16 [tap][N][C] operand layouts (once per optimizer step)."""
+        st = _abi.stream()
+        for pk in self.packs.values():
+            check(lib.sv_pack_weight(ptr(self.p(pk["wname"])), ptr(pk["w"]), pk["N"], pk["C"], pk["T"], pk["n_real"],
+                                     pk["c_real"], pk["sn"], pk["sc"], pk["st"], pk["tidx"], st))
+
+    # ---- low-level launch helpers --------------------------------------------------------------
+    def _igemm(self, ctx, key, A, pack, NB, H, W, OH, OW, in_stride=1, out=None, outf=None, res=None, bias=None, stats=None,
+               out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0):
+        a = ctx.args.get(key)
+        if a is None:
+            pk = self.packs[pack]
+            a = IgemmArgs()
+            a.Wt = ptr(pk["w"])
+            a.NB, a.H, a.W, a.C = NB, H, W, pk["C"]
+            a.OH, a.OW, a.N, a.T = OH, OW, pk["N"], pk["T"]
+            a.in_stride, a.out_stride, a.out_off_y, a.out_off_x = in_stride, out_stride, off[0], off[1]
+            a.OHf = OHf if OHf is not None else OH * out_stride
+            a.OWf = OWf if OWf is not None else OW * out_stride
+            a.n_valid, a.group_images = n_valid, ctx.B
+            a.dy, a.dx = taps_array([t[1] for t in pk["taps"]]), taps_array([t[2] for t in pk["taps"]])
+            assert A.shape[-1] == pk["C"], (key, A.shape, pk["C"])
+            ctx.args[key] = a
+        # operand pointers are refreshed on every call (callers may hand in different tensors)
+        a.A, a.out_bf16, a.out_f32, a.residual, a.bias, a.stats = ptr(A), ptr(out), ptr(outf), ptr(res), ptr(bias), ptr(stats)
+        a.impl = self.impl
+        check(lib.sv_igemm_fprop(C.byref(a), _abi.stream()))
+
+    def _wgrad(self, ctx, key, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, wname, n_real, c_real, sn, sc, st):
+        ent = ctx.args.get(key)
+        if ent is None:
+            T = len(taps)
+            bmn = 128 if N % 128 == 0 else 64 if N % 64 == 0 else 32 if N % 32 == 0 else 16
+            tiles = ((T * Cc + 127) // 128) * ((N + bmn - 1) // bmn)
+            M = NB * OH * OW
+            splits = max(1, min((296 + tiles - 1) // tiles, max(1, M // 256)))
+            while splits > 1 and splits * N * T * Cc > self.wg_ws.numel():
+                splits -= 1
+            assert splits * N * T * Cc <= self.wg_ws.numel(), "wgrad workspace too small for %s" % key
+            a = WgradArgs()
+            a.partial = ptr(self.wg_ws)
+            a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = NB, H, W, Cc, OH, OW, N, T
+            a.in_stride, a.splits = in_stride, splits
+            a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
+            ent = (a, taps_array([t[0] for t in taps]), splits, T)
+            ctx.args[key] = ent
+        a, tidx, splits, T = ent
+        a.A, a.Gr = ptr(A), ptr(Gr)
+        s = _abi.stream()
+        check(lib.sv_igemm_wgrad(C.byref(a), s))
+        check(lib.sv_wgrad_reduce(ptr(self.wg_ws), ptr(self.g(wname)), splits, N, Cc, T, n_real, c_real, sn, sc, st, tidx, s))
+
+    def _bn_fwd(self, ctx, bn_name, key, stats, Cc, count):
+        """finalize batch statistics -> (scale, shift, mean, var), all [G][C]"""
+        G = ctx.G
+        rec = dict(mean=ctx.t(key + ".mean", (G, Cc), torch.float32), var=ctx.t(key + ".var", (G, Cc), torch.float32),
+                   scale=ctx.t(key + ".scale", (G, Cc), torch.float32), shift=ctx.t(key + ".shift", (G, Cc), torch.float32),
+                   count=count, C=Cc, name=bn_name)
+        check(lib.sv_bn_finalize(ptr(stats), ptr(self.p(bn_name + ".weight")), ptr(self.p(bn_name + ".bias")), float(count),
+                                 BN_EPS, G, Cc, Cc, ptr(rec["mean"]), ptr(rec["var"]), ptr(rec["scale"]), ptr(rec["shift"]),
+                                 _abi.stream()))
+        ctx.bn[bn_name] = rec
+        return rec
+
+    def _bn_act(self, ctx, y, a, rec, slope, rows_per_group):
+        check(lib.sv_bn_act_fwd(ptr(y), ptr(a), ptr(rec["scale"]), ptr(rec["shift"]), float(slope), rows_per_group, ctx.G,
+                                rec["C"], _abi.stream()))
+
+    def _bn_bwd(self, ctx, key, terms, y, addend, g_y, rows_per_group, HW):
+        """terms: list of dict(rec, g_a | g_feat, slope).  Runs the dgamma/dbeta reductions and the apply."""
+        G = ctx.G
+        Cc = terms[0]["rec"]["C"]
+        arr = (BnBwdTerm * len(terms))()
+        s = _abi.stream()
+        for i, t in enumerate(terms):
+            rec = t["rec"]
+            dg, db = ctx.z("%s.dg%d" % (key, i), G * Cc), ctx.z("%s.db%d" % (key, i), G * Cc)
+            check(lib.sv_bn_bwd_reduce(ptr(t.get("g_a")), ptr(t.get("g_feat")), ptr(y), ptr(rec["scale"]), ptr(rec["shift"]),
+                                       ptr(rec["mean"]), ptr(rec["var"]), BN_EPS, float(t["slope"]), rows_per_group, HW, G, Cc,
+                                       ptr(dg), ptr(db), s))
+            arr[i].g_a, arr[i].g_feat = ptr(t.get("g_a")), ptr(t.get("g_feat"))
+            arr[i].scale, arr[i].shift, arr[i].mean, arr[i].var = ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"])
+            arr[i].dgamma, arr[i].dbeta = ptr(dg), ptr(db)
+            arr[i].grad_gamma, arr[i].grad_beta = ptr(self.g(rec["name"] + ".weight")), ptr(self.g(rec["name"] + ".bias"))
+            arr[i].slope, arr[i].c_real = float(t["slope"]), Cc
+        check(lib.sv_bn_bwd_apply(arr, len(terms), ptr(y), ptr(addend), ptr(g_y), BN_EPS, rows_per_group, HW, G, Cc, s))
+
+    # ---- encoder -------------------------------------------------------------------------------
+    def encoder_fwd(self, ctx, x_img):
+        """x_img: bf16 NHWC [NB, 32, 32, pad16(in_ch)] -> feat fp32 [NB, feat]"""
+        topo, NB, G, B = self.topo, ctx.NB, ctx.G, ctx.B
+        slope, sslope = topo["slope"], topo["shortcut_slope"]
+        H, f0 = 32, topo["f0"]
+        ctx.x_img = x_img
+        h = ctx.t("h0", (NB, H, H, f0))
+        st = ctx.z("st.h0", G * 2 * f0)
+        self._igemm(ctx, "conv0", x_img, "conv0.f", NB, H, H, H, H, out=h, stats=st,
+                    bias=self.p("feature_extractor.encoder.pre_process.conv0.bias"))
+        ctx.tape = []
+        for ui, u in enumerate(topo["units"]):
+            k = "u%d" % ui
+            Ho = H // u.stride
+            rows_in, rows_out = B * H * H, B * Ho * Ho
+            bn1 = self._bn_fwd(ctx, u.prefix + ".f_block.norm1", k + ".bn1", st, u.cin, rows_in)
+            a1 = ctx.t(k + ".a1", (NB, H, H, u.cin))
+            self._bn_act(ctx, h, a1, bn1, slope, rows_in)
+            y1 = ctx.t(k + ".y1", (NB, Ho, Ho, u.cout))
+            st1 = ctx.z(k + ".st1", G * 2 * u.cout)
+            self._igemm(ctx, k + ".conv1", a1, k + ".conv1.f", NB, H, H, Ho, Ho, in_stride=u.stride, out=y1, stats=st1)
+            bn2 = self._bn_fwd(ctx, u.prefix + ".f_block.norm2", k + ".bn2", st1, u.cout, rows_out)
+            a2 = ctx.t(k + ".a2", (NB, Ho, Ho, u.cout))
+            self._bn_act(ctx, y1, a2, bn2, slope, rows_out)
+            bns = a_s = None
+            res = h
+            if u.shortcut:
+                bns = self._bn_fwd(ctx, u.prefix + ".i_block.norm", k + ".bns", st, u.cin, rows_in)
+                a_s = ctx.t(k + ".as", (NB, H, H, u.cin))
+                self._bn_act(ctx, h, a_s, bns, sslope, rows_in)
+                res = ctx.t(k + ".s", (NB, Ho, Ho, u.cout))
+                self._igemm(ctx, k + ".sc", a_s, k + ".sc.f", NB, H, H, Ho, Ho, in_stride=u.stride, out=res)
+            hn = ctx.t(k + ".h", (NB, Ho, Ho, u.cout))
+            stn = ctx.z(k + ".sth", G * 2 * u.cout)
+            self._igemm(ctx, k + ".conv2", a2, k + ".conv2.f", NB, Ho, Ho, Ho, Ho, out=hn, stats=stn, res=res)
+            ctx.tape.append(dict(u=u, k=k, h_in=h, H=H, Ho=Ho, bn1=bn1, a1=a1, y1=y1, bn2=bn2, a2=a2, bns=bns, a_s=a_s))
+            h, st, H = hn, stn, Ho
+        Cf = topo["feat"]
+        bnT = self._bn_fwd(ctx, "feature_extractor.encoder.transition.norm", "bnT", st, Cf, B * H * H)
+        feat = ctx.t("feat", (NB, Cf), torch.float32)
+        check(lib.sv_bn_act_gap_fwd(ptr(h), ptr(feat), ptr(bnT["scale"]), ptr(bnT["shift"]), float(slope), NB, H * H, Cf, B,
+                                    _abi.stream()))
+        ctx.enc_out = dict(h=h, H=H, bnT=bnT)
+        return feat
+
+    def encoder_bwd(self, ctx, g_feat):
+        """g_feat: fp32 [NB, feat].  Accumulates every encoder parameter gradient into the grad arena."""
+        topo, NB, G, B = self.topo, ctx.NB, ctx.G, ctx.B
+        slope, sslope = topo["slope"], topo["shortcut_slope"]
+        eo = ctx.enc_out
+        H, Cf = eo["H"], topo["feat"]
+        g_h = ctx.t("g.h.%d.%d" % (H, Cf), (NB, H, H, Cf))
+        self._bn_bwd(ctx, "bnT", [dict(rec=eo["bnT"], g_feat=g_feat, slope=slope)], eo["h"], None, g_h, B * H * H, H * H)
+        flip = 0
+        for rec in reversed(ctx.tape):
+            u, k, Hin, Ho = rec["u"], rec["k"], rec["H"], rec["Ho"]
+            rows_in, rows_out = B * Hin * Hin, B * Ho * Ho
+            g_out = g_h
+            K9 = 9
+            # conv2: weight gradient, then input gradient
+            self._wgrad(ctx, k + ".conv2.w", rec["a2"], g_out, conv_taps(3, 1), NB, Ho, Ho, u.cout, Ho, Ho, u.cout, 1,
+                        u.prefix + ".f_block.conv2.weight", u.cout, u.cout, u.cout * K9, K9, 1)
+            g_a2 = ctx.t("g.a2.%d.%d" % (Ho, u.cout), (NB, Ho, Ho, u.cout))
+            self._igemm(ctx, k + ".conv2.d", g_out, k + ".conv2.d00", NB, Ho, Ho, Ho, Ho, out=g_a2)
+            g_y1 = ctx.t("g.y1.%d.%d" % (Ho, u.cout), (NB, Ho, Ho, u.cout))
+            self._bn_bwd(ctx, k + ".bn2", [dict(rec=rec["bn2"], g_a=g_a2, slope=slope)], rec["y1"], None, g_y1, rows_out, Ho * Ho)
+            # conv1
+            self._wgrad(ctx, k + ".conv1.w", rec["a1"], g_y1, conv_taps(3, 1), NB, Hin, Hin, u.cin, Ho, Ho, u.cout, u.stride,
+                        u.prefix + ".f_block.conv1.weight", u.cout, u.cin, u.cin * K9, K9, 1)
+            g_a1 = ctx.t("g.a1.%d.%d" % (Hin, u.cin), (NB, Hin, Hin, u.cin))
+            self._dgrad(ctx, k + ".conv1", g_y1, g_a1, NB, Ho, Hin, u.stride)
+            terms = [dict(rec=rec["bn1"], g_a=g_a1, slope=slope)]
+            addend = g_out
+            if u.shortcut:
+                self._wgrad(ctx, k + ".sc.w", rec["a_s"], g_out, conv_taps(1, 0), NB, Hin, Hin, u.cin, Ho, Ho, u.cout, u.stride,
+                            u.prefix + ".i_block.conv.weight", u.cout, u.cin, u.cin, 1, 1)
+                g_as = ctx.t("g.as.%d.%d" % (Hin, u.cin), (NB, Hin, Hin, u.cin))
+                self._dgrad(ctx, k + ".sc", g_out, g_as, NB, Ho, Hin, u.stride)
+                terms.append(dict(rec=rec["bns"], g_a=g_as, slope=sslope))
+                addend = None
+            flip ^= 1
+            g_prev = ctx.t("g.h.%d.%d.%d" % (Hin, u.cin, flip), (NB, Hin, Hin, u.cin))
+            self._bn_bwd(ctx, k + ".bn1", terms, rec["h_in"], addend, g_prev, rows_in, Hin * Hin)
+            g_h = g_prev
+        # conv0: weight + bias gradient (no input gradient: the input is data)
+        f0 = topo["f0"]
+        cin_p = pad16(self.in_ch)
+        self._wgrad(ctx, "conv0.w", ctx.x_img, g_h, conv_taps(3, 1), NB, 32, 32, cin_p, 32, 32, f0, 1,
+                    "feature_extractor.encoder.pre_process.conv0.weight", f0, self.in_ch, self.in_ch * 9, 9, 1)
+        check(lib.sv_colsum_bf16(ptr(g_h), ptr(self.g("feature_extractor.encoder.pre_process.conv0.bias")), NB * 32 * 32, f0, f0,
+                                 _abi.stream()))
+
+    def _dgrad(self, ctx, key, g_out, g_in, NB, Ho, Hin, stride):
+        """input gradient of a conv by output-parity phases (stride 1: a single phase)"""
+        s = stride
+        phases = [(py, px) for py in range(s) for px in range(s) if ("%s.d%d%d" % (key, py, px)) in self.packs]
+        if len(phases) < s * s:
+            g_in.zero_()
+        for py, px in phases:
+            self._igemm(ctx, "%s.d%d%d" % (key, py, px), g_out, "%s.d%d%d" % (key, py, px), NB, Ho, Ho, Ho, Ho, out=g_in,
+                        out_stride=s, off=(py, px), OHf=Hin, OWf=Hin)
+
+    # ---- heads + sample ------------------------------------------------------------------------
+    HEADS = (("continuous_inference.mean", "mu"), ("continuous_inference.log_sigma", "ls"), ("disc_latent_inference", "logits"))
+
+    def heads_fwd(self, ctx, feat):
+        NB, Cf = ctx.NB, self.topo["feat"]
+        s = _abi.stream()
+        outs = {}
+        for hname, short in self.HEADS:
+            n = self.nd if short == "logits" else self.ldc
+            o = ctx.t(short, (NB, n), torch.float32)
+            check(lib.sv_linear_fwd(ptr(feat), Cf, ptr(self.p(hname + ".fc.weight")), Cf, 0, ptr(self.p(hname + ".fc.bias")),
+                                    ptr(o), None, n, None, 0, NB, n, Cf, s))
+            outs[short] = o
+        la = ctx.t("la", (NB, self.nd), torch.float32)
+        check(lib.sv_log_softmax_fwd(ptr(outs["logits"]), ptr(la), NB, self.nd, s))
+        ctx.feat = feat
+        return outs["mu"], outs["ls"], la
+
+    def heads_bwd(self, ctx, g_mu, g_ls, g_la):
+        """returns g_feat fp32 [NB, feat]; accumulates head parameter gradients"""
+        NB, Cf = ctx.NB, self.topo["feat"]
+        s = _abi.stream()
+        g_logits = ctx.t("g.logits", (NB, self.nd), torch.float32)
+        check(lib.sv_log_softmax_bwd(ptr(g_la), ptr(ctx.bufs["la"]), ptr(g_logits), NB, self.nd, s))
+        g_feat = ctx.t("g.feat", (NB, Cf), torch.float32)
+        first = True
+        for (hname, short), g in zip(self.HEADS, (g_mu, g_ls, g_logits)):
+            n = self.nd if short == "logits" else self.ldc
+            check(lib.sv_linear_bwd_weight(ptr(g), None, n, ptr(ctx.feat), Cf, ptr(self.g(hname + ".fc.weight")), Cf, 0,
+                                           ptr(self.g(hname + ".fc.bias")), NB, n, Cf, s))
+            check(lib.sv_linear_bwd_input(ptr(g), None, n, ptr(self.p(hname + ".fc.weight")), Cf, 0, ptr(g_feat), Cf,
+                                          0 if first else 1, NB, n, Cf, s))
+            first = False
+        return g_feat
+
+    def sample_fwd(self, ctx, group, mode, eps, unif=None, label=None, label_mix=None, lam_dev=None):
+        """Sample.forward (vae.py:23-56) for one pass group; eps/unif are device tensors [B, .]"""
+        B, D, nd = ctx.B, self.ldc, self.nd
+        lat = ctx.t("latent", (ctx.NB, self.latent), torch.float32)
+        r0 = group * B
+        mu, ls, la = ctx.bufs["mu"], ctx.bufs["ls"], ctx.bufs["la"]
+        check(lib.sv_sample_fwd(ptr(mu[r0:]), ptr(ls[r0:]), ptr(la[r0:]), ptr(eps), ptr(unif), ptr(label), ptr(label_mix),
+                                ptr(lam_dev), mode, self.temperature, B, D, nd, ptr(lat[r0:]), self.latent, _abi.stream()))
+        ctx.sample = getattr(ctx, "sample", {})
+        ctx.sample[group] = dict(mode=mode, eps=eps)
+        return lat
+
+    def sample_bwd(self, ctx, group, g_latent, g_mu, g_ls, g_la, accumulate=1):
+        B, D, nd = ctx.B, self.ldc, self.nd
+        r0 = group * B
+        sm = ctx.sample[group]
+        lat = ctx.bufs["latent"]
+        check(lib.sv_sample_bwd(ptr(g_latent[r0:]), self.latent, ptr(ctx.bufs["ls"][r0:]), ptr(sm["eps"]), ptr(lat[r0:]),
+                                sm["mode"], self.temperature, B, D, nd, ptr(g_mu[r0:]), ptr(g_ls[r0:]),
+                                ptr(g_la[r0:]) if g_la is not None else None, accumulate, _abi.stream()))
+
+    # ---- decoder -------------------------------------------------------------------------------
+    def decoder_fwd(self, ctx, latent):
+        """latent fp32 [NB, ldc+nd] -> reconstruction logits fp32 NHWC [NB, 32, 32, in_ch]"""
+        NB, G, B = ctx.NB, ctx.G, ctx.B
+        s = _abi.stream()
+        c0 = DEC_CHANNELS[0]
+        y = ctx.t("d0.y", (NB, 1, 1, c0))
+        st = ctx.z("d0.st", G * 2 * c0)
+        check(lib.sv_linear_fwd(ptr(latent), self.latent, ptr(self.p("feature_reconstructor.decoder.0.weight")), c0, 1, None,
+                                None, ptr(y), c0, ptr(st), B, NB, c0, self.latent, s))
+        ctx.dec = []
+        ctx.dec_latent = latent
+        cin, hin = c0, 1
+        for li in range(5):
+            bn = self._bn_fwd(ctx, "feature_reconstructor.decoder.%d" % (3 * li + 1), "d%d.bn" % li, st, cin, B * hin * hin)
+            a = ctx.t("d%d.a" % li, (NB, hin, hin, cin))
+            self._bn_act(ctx, y, a, bn, 0.0, B * hin * hin)
+            ctx.dec.append(dict(y=y, a=a, bn=bn, hin=hin, cin=cin))
+            last = li == 4
+            cout = self.in_ch if last else DEC_CHANNELS[li + 1]
+            ho = hin * 2
+            if last:
+                yn, stn = ctx.t("rec", (NB, ho, ho, cout), torch.float32), None
+            else:
+                yn, stn = ctx.t("d%d.y" % (li + 1), (NB, ho, ho, cout)), ctx.z("d%d.st" % (li + 1), G * 2 * cout)
+            for py in range(2):
+                for px in range(2):
+                    self._igemm(ctx, "d%d.f%d%d" % (li + 1, py, px), a, "d%d.f%d%d" % (li + 1, py, px), NB, hin, hin, hin, hin,
+                                out=None if last else yn, outf=yn if last else None, stats=stn, out_stride=2, off=(py, px),
+                                OHf=ho, OWf=ho, n_valid=cout if last else 0)
+            y, st, cin, hin = yn, stn, cout, ho
+        return y
+
+    def decoder_bwd(self, ctx, g_rec):
+        """g_rec: bf16 NHWC [NB, 32, 32, pad16(in_ch)] -> g_latent fp32 [NB, latent]"""
+        NB, G, B = ctx.NB, ctx.G, ctx.B
+        s = _abi.stream()
+        g = g_rec
+        cout, cout_p = self.in_ch, pad16(self.in_ch)
+        for li in range(4, -1, -1):
+            d = ctx.dec[li]
+            hin, cin, ho = d["hin"], d["cin"], d["hin"] * 2
+            wname = "feature_reconstructor.decoder.%d.weight" % (3 * (li + 1))
+            taps = self.packs["d%d.d" % (li + 1)]["taps"]
+            # ConvT weight gradient: rows = coarse input pixels, Gr = a_in (N = cin), A = g_out (C = cout)
+            self._wgrad(ctx, "d%d.w" % (li + 1), g, d["a"], taps, NB, ho, ho, cout_p, hin, hin, cin, 2, wname, cin, cout,
+                        cout * 16, 16, 1)
+            g_a = ctx.t("g.d%d.a" % li, (NB, hin, hin, cin))
+            self._igemm(ctx, "d%d.d" % (li + 1), g, "d%d.d" % (li + 1), NB, ho, ho, hin, hin, in_stride=2, out=g_a)
+            g_y = ctx.t("g.d%d.y" % li, (NB, hin, hin, cin))
+            self._bn_bwd(ctx, "d%d.bn" % li, [dict(rec=d["bn"], g_a=g_a, slope=0.0)], d["y"], None, g_y, B * hin * hin, hin * hin)
+            g, cout, cout_p = g_y, cin, cin
+        c0 = DEC_CHANNELS[0]
+        w0 = "feature_reconstructor.decoder.0.weight"
+        check(lib.sv_linear_bwd_weight(None, ptr(g), c0, ptr(ctx.dec_latent), self.latent, ptr(self.g(w0)), c0, 1, None, NB, c0,
+                                       self.latent, s))
+        g_lat = ctx.t("g.latent", (NB, self.latent), torch.float32)
+        check(lib.sv_linear_bwd_input(None, ptr(g), c0, ptr(self.p(w0)), c0, 1, ptr(g_lat), self.latent, 0, NB, c0, self.latent, s))
+        return g_lat
+
+    # ---- BatchNorm running statistics ----------------------------------------------------------
+    def bn_running_update(self, passes):
+        """passes: list of (ctx, group) in the order the reference would have executed the forwards
+        (P1, P2, P3, P4 for a SHOT step).  Only BNs that ran in a pass are updated for it."""
+        s = _abi.stream()
+        names = []
+        for ctx, _ in passes:
+            for n in ctx.bn:
+                if n not in names:
+                    names.append(n)
+        for n in names:
+            ps = [(c, gi) for c, gi in passes if n in c.bn]
+            rec0 = ps[0][0].bn[n]
+            Cc = rec0["C"]
+            mp = (C.c_void_p * len(ps))(*[c.bn[n]["mean"][gi].data_ptr() for c, gi in ps])
+            vp_ = (C.c_void_p * len(ps))(*[c.bn[n]["var"][gi].data_ptr() for c, gi in ps])
+            check(lib.sv_bn_running_update(mp, vp_, len(ps), float(rec0["count"]), BN_MOMENTUM, Cc, ptr(self.b(n + ".running_mean")),
+                                           ptr(self.b(n + ".running_var")), ptr(self.b(n + ".num_batches_tracked")), s))
+
+    def zero_grads(self):
+        self.grads.zero_()

@@ -146,6 +146,8 @@ def run_case(M, case):
                 kl[i, j] = gk(mu[i], ls[i], mu[j], ls[j])
         idx = torch.topk(kl, 2, largest=False)[1][:, 1]
         g["om_index"] = idx.tolist()
+        g["om_mu"] = mu.tolist()          # the full FP32 latents the pairing was computed on, so the CUDA
+        g["om_ls"] = ls.tolist()          # kernel can be checked for bit-exact indices on the GPU box
         g["om_oracle_matrix_bitexact"] = bool(torch.equal(kl, O.pairwise_kl_matrix(mu, ls)))
         g["om_oracle_index_equal"] = bool(torch.equal(idx, O.optimal_match_index(mu, ls)))
         srt = torch.sort(kl, dim=1)[0]

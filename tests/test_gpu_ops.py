@@ -1,0 +1,416 @@
+"""GPU parity tests, kernel level: every libshotvae entry point against the CPU oracle / plain torch
+FP32 on the same seeded inputs.  Tolerances: index and integer results bit-exact; FP32 kernels 1e-5
+relative; bf16-operand GEMMs are compared on bf16-rounded inputs with FP32 accumulation, so only
+the accumulation order differs (tolerance 2e-3 of the output RMS, bf16 output rounding included)."""
+import ctypes as C
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sv():
+    from shotvae_b200 import _abi
+    return _abi
+
+
+def dev(t):
+    return t.cuda()
+
+
+def rel_rms(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / max(b.norm(), 1e-30))
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def nhwc(x):           # NCHW fp32 -> NHWC bf16 cuda
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def from_nhwc(x):      # NHWC cuda -> NCHW fp32 cpu
+    return x.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def pack(sv, w, N, Cc, taps, n_real, c_real, sn, sc, st):
+    from shotvae_b200._abi import lib, check, ptr, taps_array
+    dst = torch.zeros(len(taps), N, Cc, dtype=torch.bfloat16, device="cuda")
+    wd = w.contiguous().cuda()
+    check(lib.sv_pack_weight(ptr(wd), ptr(dst), N, Cc, len(taps), n_real, c_real, sn, sc, st, taps_array([t[0] for t in taps]),
+                             sv.stream()))
+    return dst
+
+
+def igemm(sv, A, Wt, taps, NB, H, W, Cc, OH, OW, N, in_stride=1, out=None, outf=None, res=None, bias=None, stats=None,
+          out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0, group_images=None, impl=1):
+    from shotvae_b200._abi import lib, check, ptr, taps_array, IgemmArgs
+    a = IgemmArgs()
+    a.A, a.Wt, a.out_bf16, a.out_f32, a.residual, a.bias, a.stats = ptr(A), ptr(Wt), ptr(out), ptr(outf), ptr(res), ptr(bias), ptr(stats)
+    a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = NB, H, W, Cc, OH, OW, N, len(taps)
+    a.in_stride, a.out_stride, a.out_off_y, a.out_off_x = in_stride, out_stride, off[0], off[1]
+    a.OHf, a.OWf = OHf or OH * out_stride, OWf or OW * out_stride
+    a.n_valid, a.group_images = n_valid, group_images or NB
+    a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
+    a.impl = impl
+    check(lib.sv_igemm_fprop(C.byref(a), sv.stream()))
+
+
+IMPLS = [1]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("cin,cout,H,stride,k,NB", [
+    (32, 32, 32, 1, 3, 4), (16, 32, 32, 1, 3, 3), (32, 64, 32, 2, 3, 4), (64, 64, 16, 1, 3, 8), (64, 128, 16, 2, 3, 8),
+    (128, 128, 8, 1, 3, 16), (16, 32, 32, 1, 1, 2), (32, 64, 32, 2, 1, 4), (160, 160, 8, 1, 3, 2), (16, 16, 32, 1, 3, 5)])
+def test_conv_fprop_matches_torch(sv, impl, cin, cout, H, stride, k, NB):
+    from shotvae_b200.plan import conv_taps
+    torch.manual_seed(cin * 1000 + cout + H + stride)
+    x, w = bf(torch.randn(NB, cin, H, H)), bf(torch.randn(cout, cin, k, k) * 0.1)
+    bias, resid = torch.randn(cout), bf(torch.randn(NB, cout, H // stride, H // stride))
+    want = F.conv2d(x, w, bias, stride, k // 2) + resid
+    taps = conv_taps(k, k // 2)
+    Wt = pack(sv, w, cout, cin, taps, cout, cin, cin * k * k, k * k, 1)
+    Ho = H // stride
+    out = torch.empty(NB, Ho, Ho, cout, dtype=torch.bfloat16, device="cuda")
+    G = 1 if NB % 2 else 2
+    stats = torch.zeros(G, 2, cout, device="cuda")
+    igemm(sv, nhwc(x), Wt, taps, NB, H, H, cin, Ho, Ho, cout, in_stride=stride, out=out, res=nhwc(resid), bias=bias.cuda(),
+          stats=stats, group_images=NB // G, impl=impl)
+    got = from_nhwc(out)
+    assert rel_rms(got, want) < 4e-3
+    gq = got.view(G, NB // G, cout, -1)
+    assert rel_rms(stats[:, 0].cpu(), gq.sum(dim=(1, 3))) < 2e-3
+    assert rel_rms(stats[:, 1].cpu(), (gq * gq).sum(dim=(1, 3))) < 1e-3
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("cin,cout,Hin,NB", [(1024, 512, 1, 8), (512, 256, 2, 4), (128, 64, 8, 4), (64, 3, 16, 4)])
+def test_convT_fprop_phases_match_torch(sv, impl, cin, cout, Hin, NB):
+    from shotvae_b200.plan import dgrad_phase_taps, live_taps, pad16
+    torch.manual_seed(cin + cout)
+    x, w = bf(torch.randn(NB, cin, Hin, Hin)), bf(torch.randn(cin, cout, 4, 4) * 0.05)
+    want = F.conv_transpose2d(x, w, None, 2, 1)
+    cp, Ho = pad16(cout), 2 * Hin
+    out = torch.zeros(NB, Ho, Ho, cp, dtype=torch.bfloat16, device="cuda")
+    outf = torch.zeros(NB, Ho, Ho, cout, dtype=torch.float32, device="cuda")
+    A = nhwc(x)
+    for (py, px), taps in dgrad_phase_taps(4, 2, 1).items():
+        taps = live_taps(taps, Hin, Hin, Hin, Hin, 1)
+        Wt = pack(sv, w, cp, cin, taps, cout, cin, 16, cout * 16, 1)
+        igemm(sv, A, Wt, taps, NB, Hin, Hin, cin, Hin, Hin, cp, out=out, outf=outf, out_stride=2, off=(py, px), OHf=Ho, OWf=Ho,
+              n_valid=cout, impl=impl)
+    assert rel_rms(from_nhwc(out)[:, :cout], want) < 4e-3
+    assert rel_rms(from_nhwc(outf), want) < 1e-3
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("cin,cout,H,stride,k,NB", [(32, 32, 16, 1, 3, 4), (32, 64, 32, 2, 3, 4), (32, 64, 32, 2, 1, 4), (16, 32, 8, 1, 1, 4)])
+def test_conv_dgrad_phases_match_autograd(sv, impl, cin, cout, H, stride, k, NB):
+    from shotvae_b200.plan import dgrad_phase_taps, live_taps
+    torch.manual_seed(7 + cin + stride)
+    x = torch.randn(NB, cin, H, H, requires_grad=True)
+    w = bf(torch.randn(cout, cin, k, k) * 0.1)
+    Ho = H // stride
+    g = bf(torch.randn(NB, cout, Ho, Ho))
+    F.conv2d(x, w, None, stride, k // 2).backward(g)
+    gin = torch.zeros(NB, H, H, cin, dtype=torch.bfloat16, device="cuda")
+    G_ = nhwc(g)
+    for (py, px), taps in dgrad_phase_taps(k, stride, k // 2).items():
+        taps = live_taps(taps, Ho, Ho, Ho, Ho, 1)
+        if not taps:
+            continue
+        Wt = pack(sv, w, cin, cout, taps, cin, cout, k * k, cin * k * k, 1)
+        igemm(sv, G_, Wt, taps, NB, Ho, Ho, cout, Ho, Ho, cin, out=gin, out_stride=stride, off=(py, px), OHf=H, OWf=H, impl=impl)
+    assert rel_rms(from_nhwc(gin), x.grad) < 4e-3
+
+
+def wgrad(sv, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, grad, n_real, c_real, sn, sc, st, splits):
+    from shotvae_b200._abi import lib, check, ptr, taps_array, WgradArgs
+    T = len(taps)
+    ws = torch.empty(splits * N * T * Cc, device="cuda")
+    a = WgradArgs()
+    a.A, a.Gr, a.partial = ptr(A), ptr(Gr), ptr(ws)
+    a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T, a.in_stride, a.splits = NB, H, W, Cc, OH, OW, N, T, in_stride, splits
+    a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
+    check(lib.sv_igemm_wgrad(C.byref(a), sv.stream()))
+    check(lib.sv_wgrad_reduce(ptr(ws), ptr(grad), splits, N, Cc, T, n_real, c_real, sn, sc, st, taps_array([t[0] for t in taps]),
+                              sv.stream()))
+
+
+@pytest.mark.parametrize("cin,cout,H,stride,k,NB,splits", [(32, 32, 16, 1, 3, 4, 3), (32, 64, 32, 2, 3, 4, 5), (16, 32, 16, 1, 1, 4, 1),
+                                                           (128, 128, 8, 1, 3, 8, 2), (160, 160, 8, 1, 3, 2, 1), (16, 16, 32, 1, 3, 2, 7)])
+def test_conv_wgrad_matches_autograd(sv, cin, cout, H, stride, k, NB, splits):
+    from shotvae_b200.plan import conv_taps
+    torch.manual_seed(11 + cin + stride + k)
+    x = bf(torch.randn(NB, cin, H, H))
+    w = torch.randn(cout, cin, k, k, requires_grad=True)
+    Ho = H // stride
+    g = bf(torch.randn(NB, cout, Ho, Ho))
+    F.conv2d(x, w, None, stride, k // 2).backward(g)
+    grad = torch.ones(cout, cin, k, k, device="cuda")      # the kernel accumulates (+=)
+    wgrad(sv, nhwc(x), nhwc(g).view(-1, cout), conv_taps(k, k // 2), NB, H, H, cin, Ho, Ho, cout, stride, grad, cout, cin,
+          cin * k * k, k * k, 1, splits)
+    assert rel_rms(grad.cpu() - 1.0, w.grad) < 2e-3
+
+
+@pytest.mark.parametrize("cin,cout,Hin,NB", [(1024, 512, 1, 8), (128, 64, 8, 4), (64, 3, 16, 4)])
+def test_convT_wgrad_and_dgrad_match_autograd(sv, cin, cout, Hin, NB):
+    from shotvae_b200.plan import conv_taps, live_taps, pad16
+    torch.manual_seed(13 + cin)
+    x = bf(torch.randn(NB, cin, Hin, Hin)).requires_grad_(True)
+    w = bf(torch.randn(cin, cout, 4, 4) * 0.05).requires_grad_(True)
+    Ho, cp = 2 * Hin, pad16(cout)
+    g = bf(torch.randn(NB, cout, Ho, Ho))
+    F.conv_transpose2d(x, w, None, 2, 1).backward(g)
+    gp = torch.zeros(NB, cp, Ho, Ho)
+    gp[:, :cout] = g
+    Gd = nhwc(gp)
+    taps = live_taps(conv_taps(4, 1), Hin, Hin, Ho, Ho, 2)
+    grad = torch.zeros(cin, cout, 4, 4, device="cuda")
+    wgrad(sv, Gd, nhwc(x.detach()).view(-1, cin), taps, NB, Ho, Ho, cp, Hin, Hin, cin, 2, grad, cin, cout, cout * 16, 16, 1, 2)
+    assert rel_rms(grad.cpu(), w.grad) < 2e-3
+    Wt = pack(sv, w.detach(), cin, cp, taps, cin, cout, cout * 16, 16, 1)
+    gin = torch.zeros(NB, Hin, Hin, cin, dtype=torch.bfloat16, device="cuda")
+    igemm(sv, Gd, Wt, taps, NB, Ho, Ho, cp, Hin, Hin, cin, in_stride=2, out=gin)
+    assert rel_rms(from_nhwc(gin), x.grad) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm
+@pytest.mark.parametrize("Cc,HW,B,G,slope", [(32, 64, 8, 2, 0.01), (160, 16, 4, 1, 0.0), (1024, 1, 16, 2, 0.0), (16, 1024, 4, 1, 1.0)])
+def test_bn_act_forward_backward(sv, Cc, HW, B, G, slope):
+    from shotvae_b200._abi import lib, check, ptr, BnBwdTerm
+    torch.manual_seed(Cc + HW)
+    NB = G * B
+    y = bf(torch.randn(NB, HW, Cc) * 2 + 0.5)
+    gamma, beta = torch.rand(Cc) + 0.5, torch.randn(Cc) * 0.1
+    g_a = bf(torch.randn(NB, HW, Cc))
+    addend = bf(torch.randn(NB, HW, Cc))
+    # torch reference, per group
+    wants, gys, dgs, dbs = [], [], [], []
+    gam_ref = gamma.clone().requires_grad_(True)
+    bet_ref = beta.clone().requires_grad_(True)
+    for g in range(G):
+        yy = y[g * B:(g + 1) * B].reshape(-1, Cc).clone().requires_grad_(True)
+        o = F.batch_norm(yy, None, None, gam_ref, bet_ref, True, 0.1, 1e-5)
+        o = torch.where(o > 0, o, o * slope)
+        wants.append(o.detach())
+        o.backward(g_a[g * B:(g + 1) * B].reshape(-1, Cc))
+        gys.append(yy.grad + addend[g * B:(g + 1) * B].reshape(-1, Cc))
+    st = sv.stream()
+    yd = y.to(torch.bfloat16).cuda()
+    stats = torch.stack([torch.stack([y[g * B:(g + 1) * B].sum(dim=(0, 1)), (y[g * B:(g + 1) * B] ** 2).sum(dim=(0, 1))]) for g in range(G)]).cuda()
+    mean, var, scale, shift = (torch.empty(G, Cc, device="cuda") for _ in range(4))
+    check(lib.sv_bn_finalize(ptr(stats), ptr(gamma.cuda()), ptr(beta.cuda()), float(B * HW), 1e-5, G, Cc, Cc, ptr(mean), ptr(var),
+                             ptr(scale), ptr(shift), st))
+    a = torch.empty_like(yd)
+    check(lib.sv_bn_act_fwd(ptr(yd), ptr(a), ptr(scale), ptr(shift), slope, B * HW, G, Cc, st))
+    assert rel_rms(a.float().cpu().view(-1, Cc), torch.cat(wants)) < 4e-3
+    dg, db = torch.zeros(G, Cc, device="cuda"), torch.zeros(G, Cc, device="cuda")
+    gad = g_a.to(torch.bfloat16).cuda()
+    check(lib.sv_bn_bwd_reduce(ptr(gad), None, ptr(yd), ptr(scale), ptr(shift), ptr(mean), ptr(var), 1e-5, slope, B * HW, HW, G, Cc,
+                               ptr(dg), ptr(db), st))
+    assert rel_rms(dg.sum(0).cpu(), gam_ref.grad) < 1e-3
+    assert rel_rms(db.sum(0).cpu(), bet_ref.grad) < 1e-3
+    gg, gb = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    term = (BnBwdTerm * 1)()
+    term[0].g_a, term[0].scale, term[0].shift, term[0].mean, term[0].var = ptr(gad), ptr(scale), ptr(shift), ptr(mean), ptr(var)
+    term[0].dgamma, term[0].dbeta, term[0].grad_gamma, term[0].grad_beta = ptr(dg), ptr(db), ptr(gg), ptr(gb)
+    term[0].slope, term[0].c_real = slope, Cc
+    gy = torch.empty_like(yd)
+    check(lib.sv_bn_bwd_apply(term, 1, ptr(yd), ptr(addend.to(torch.bfloat16).cuda()), ptr(gy), 1e-5, B * HW, HW, G, Cc, st))
+    assert rel_rms(gy.float().cpu().view(-1, Cc), torch.cat(gys)) < 6e-3
+    assert rel_rms(gg.cpu(), gam_ref.grad) < 1e-3 and rel_rms(gb.cpu(), bet_ref.grad) < 1e-3
+
+
+# ------------------------------------------------------------------------------ loss / sample / mixup
+def test_vae_criterion_matches_oracle(sv):
+    from oracle import shotvae_oracle as O
+    from lib.criterion import VAECriterion, ClsCriterion
+    torch.manual_seed(3)
+    B, nd = 32, 10
+    for bce in (True, False):
+        x = torch.rand(B, 3, 32, 32)
+        xr = (torch.randn(B, 3, 32, 32) * 2).requires_grad_(True)
+        mu, ls = torch.randn(B, 128).requires_grad_(True), (torch.randn(B, 128) * 0.3).requires_grad_(True)
+        la = F.log_softmax(torch.randn(B, nd), 1).requires_grad_(True)
+        want = O.vae_criterion(x, xr, mu, ls, la, nd, 1.0, bce)
+        (want[0] * 0.3 + want[1] * 1.7 - want[2] * 2.0).backward()
+        d = [t.detach().cuda().requires_grad_(True) for t in (xr, mu, ls, la)]
+        got = VAECriterion(nd, 1, bce).cuda()(x.cuda(), *d)
+        (got[0] * 0.3 + got[1] * 1.7 - got[2] * 2.0).backward()
+        for gv, wv in zip(got, want):
+            assert abs(float(gv) - float(wv)) <= 1e-5 * abs(float(wv))
+        for gt, wt in zip(d, (xr, mu, ls, la)):
+            assert rel_rms(gt.grad, wt.grad) < 1e-5
+    # NHWC-backed reconstruction view (what the VAE returns internally)
+    xr2 = xr.detach().permute(0, 2, 3, 1).contiguous().cuda().permute(0, 3, 1, 2).requires_grad_(True)
+    got = VAECriterion(nd, 1, False).cuda()(x.cuda(), xr2, d[1], d[2], d[3])
+    assert abs(float(got[0]) - float(want[0])) <= 1e-5 * abs(float(want[0]))
+    pred = F.log_softmax(torch.randn(B, nd), 1).requires_grad_(True)
+    tgt = torch.rand(B, nd)
+    w = O.cls_criterion(pred, tgt)
+    w.backward()
+    pd = pred.detach().cuda().requires_grad_(True)
+    gv = ClsCriterion()(pd, tgt.cuda())
+    gv.backward()
+    assert abs(float(gv) - float(w)) < 1e-5 * abs(float(w)) and rel_rms(pd.grad, pred.grad) < 1e-5
+
+
+def test_sample_forward_backward_matches_oracle(sv):
+    from oracle import shotvae_oracle as O
+    from shotvae_b200._abi import lib, check, ptr
+    torch.manual_seed(5)
+    B, D, nd, T = 16, 128, 10, 0.67
+    for mode in (0, 1, 2):
+        mu, ls = torch.randn(B, D).requires_grad_(True), (torch.randn(B, D) * 0.3).requires_grad_(True)
+        la = F.log_softmax(torch.randn(B, nd), 1).requires_grad_(True)
+        eps, unif = torch.randn(B, D), torch.rand(B, nd)
+        lab, lab2, lam = torch.randint(0, nd, (B,)), torch.randint(0, nd, (B,)), 0.3
+        log = [("randn", eps)] + ([("rand", unif)] if mode == 2 else [])
+        want = O.sample_latent(mu, ls, la, O.ReplayDraws(log), T, None if mode == 2 else lab, mode == 1, lab2, lam).view(B, -1)
+        gl = torch.randn(B, D + nd)
+        want.backward(gl)
+        lat = torch.empty(B, D + nd, device="cuda")
+        lam_dev = torch.tensor([lam, 1 - lam], dtype=torch.float32).cuda()
+        md, lsd, lad = mu.detach().cuda(), ls.detach().cuda(), la.detach().cuda()
+        epd, und = eps.cuda(), unif.cuda()
+        check(lib.sv_sample_fwd(ptr(md), ptr(lsd), ptr(lad), ptr(epd), ptr(und), ptr(lab.cuda()), ptr(lab2.cuda()), ptr(lam_dev), mode, T,
+                                B, D, nd, ptr(lat), D + nd, sv.stream()))
+        assert rel_rms(lat, want.detach()) < 1e-5
+        g_mu, g_ls, g_la = (torch.zeros_like(t) for t in (md, lsd, lad))
+        check(lib.sv_sample_bwd(ptr(gl.cuda()), D + nd, ptr(lsd), ptr(epd), ptr(lat), mode, T, B, D, nd, ptr(g_mu), ptr(g_ls), ptr(g_la),
+                                1, sv.stream()))
+        assert rel_rms(g_mu, mu.grad) < 1e-5 and rel_rms(g_ls, ls.grad) < 1e-5
+        if mode == 2:
+            assert rel_rms(g_la, la.grad) < 1e-4
+
+
+def test_mixup_and_label_smoothing_match_oracle(sv):
+    from oracle import shotvae_oracle as O
+    import lib.utils.mixup as MX
+    B, nd = 24, 10
+    torch.manual_seed(9)
+    img, mu, ls = torch.rand(B, 3, 32, 32), torch.randn(B, 128), torch.randn(B, 128) * 0.3
+    la, lab = F.log_softmax(torch.randn(B, nd), 1), torch.randint(0, nd, (B,))
+    for fn in ("mixup", "smooth"):
+        torch.manual_seed(21); np.random.seed(21)
+        d = O.LiveDraws()
+        want = O.mixup_vae_data(img, mu, ls, la, d) if fn == "mixup" else O.label_smoothing(img, mu, ls, la, d, 0.1, lab)
+        torch.manual_seed(21); np.random.seed(21)
+        args = [t.cuda() for t in (img, mu, ls, la)]
+        got = MX.mixup_vae_data(*args) if fn == "mixup" else MX.label_smoothing(*args, epsilon=0.1, disc_label=lab.cuda())
+        for i in range(4):
+            assert torch.equal(got[i].cpu(), want[i]) or rel_rms(got[i], want[i]) < 1e-6, (fn, i)
+        if fn == "mixup":
+            assert got[4] == want[4]
+        else:
+            assert torch.equal(got[4].cpu(), want[4]) and got[5] == want[5]
+
+
+def test_om_pairing_bit_exact_vs_reference_golden(sv):
+    import lib.utils.mixup as MX
+    from oracle import shotvae_oracle as O
+    path = os.path.join(os.path.dirname(__file__), "golden", "c2_wrn28x2_nd10_b32_e400_om.json")
+    g = json.load(open(path))
+    mu, ls = torch.tensor(g["om_mu"]), torch.tensor(g["om_ls"])
+    idx, kl = MX.optimal_match_index(mu.cuda(), ls.cuda(), return_matrix=True)
+    assert idx.cpu().tolist() == g["om_index"]                       # the reference's own loop (mixup.py:11-18)
+    ref = O.pairwise_kl_matrix(mu, ls)
+    assert float((kl.cpu() - ref).abs().max()) < 0.25 * g["om_min_gap_2nd_3rd"]
+    assert torch.all(torch.diagonal(kl.cpu()) == 0)
+    # larger seeded cases against the oracle: N(0,1) latents and near-duplicate latents
+    for B, seed, scale in ((128, 1, 1.0), (128, 2, 0.05), (200, 3, 0.3), (2, 4, 1.0)):
+        gen = torch.Generator().manual_seed(seed)
+        mu, ls = torch.randn(B, 128, generator=gen) * scale, torch.randn(B, 128, generator=gen) * 0.1 * scale
+        want = O.optimal_match_index(mu, ls)
+        got = MX.optimal_match_index(mu.cuda(), ls.cuda())
+        assert got.cpu().tolist() == want.tolist(), (B, seed)
+
+
+def test_posterior_and_inference_kl_match_oracle(sv):
+    from oracle import shotvae_oracle as O
+    from shotvae_b200._abi import lib, check, ptr
+    torch.manual_seed(17)
+    B, D, nd, lam = 32, 128, 10, 0.35
+    la = F.log_softmax(torch.randn(B, nd), 1).requires_grad_(True)
+    mu, ls = torch.randn(B, D).requires_grad_(True), (torch.randn(B, D) * 0.3).requires_grad_(True)
+    mu_t, sig_t = torch.randn(B, D), torch.rand(B, D) + 0.5
+    la_, lb_ = torch.randint(0, nd, (B,)), torch.randint(0, nd, (B,))
+    oh = lambda y: torch.zeros(B, nd).scatter_(1, y.view(-1, 1), 1)
+    disc = lam * O.cls_criterion(la, oh(la_)) + (1 - lam) * O.cls_criterion(la, oh(lb_))
+    cont = (F.mse_loss(mu, mu_t, reduction="sum") + F.mse_loss(torch.exp(ls), sig_t, reduction="sum")) / B
+    cd, cc = 1.3, 0.07
+    (cd * disc + cc * cont).backward()
+    terms = torch.zeros(2, device="cuda")
+    g_la, g_mu, g_ls = torch.zeros(B, nd, device="cuda"), torch.zeros(B, D, device="cuda"), torch.zeros(B, D, device="cuda")
+    coef = torch.tensor([cd, cc], device="cuda")
+    lam_dev = torch.tensor([lam, 1 - lam], dtype=torch.float32).cuda()
+    check(lib.sv_posterior_fwd_bwd(ptr(la.detach().cuda()), None, ptr(la_.cuda()), ptr(lb_.cuda()), ptr(lam_dev), ptr(mu.detach().cuda()),
+                                   ptr(ls.detach().cuda()), ptr(mu_t.cuda()), ptr(sig_t.cuda()), ptr(coef), B, D, nd, ptr(terms), ptr(g_la),
+                                   ptr(g_mu), ptr(g_ls), 0, sv.stream()))
+    assert abs(float(terms[0]) - float(disc)) < 1e-5 * abs(float(disc)) and abs(float(terms[1]) - float(cont)) < 1e-5 * float(cont)
+    assert rel_rms(g_la, la.grad) < 1e-5 and rel_rms(g_mu, mu.grad) < 1e-5 and rel_rms(g_ls, ls.grad) < 1e-5
+    lab = torch.randint(0, nd, (B,))
+    lsu = torch.zeros(B, nd).scatter_(1, lab.view(-1, 1), 1 - 0.001 - 0.001 / (nd - 1)) + 0.001 / (nd - 1)
+    au = torch.exp(la.detach())
+    want = float(torch.sum(au * la.detach() - au * torch.log(lsu)) / B)
+    out = torch.zeros(1, device="cuda")
+    check(lib.sv_inference_kl(ptr(la.detach().cuda()), ptr(lab.cuda()), B, nd, ptr(out), sv.stream()))
+    assert abs(float(out) - want) < 1e-5 * abs(want)
+
+
+def test_sgd_matches_oracle(sv):
+    from shotvae_b200._abi import lib, check, ptr
+    torch.manual_seed(23)
+    n = 100003
+    p, g, m = torch.randn(n + 1), torch.randn(n + 1), torch.randn(n + 1)
+    for first in (1.0, 0.0):
+        d = g * 0.5 + 5e-4 * p
+        mm = d if first else 0.9 * m + d
+        want_p = p - 0.1 * mm
+        pd, gd, md = p.cuda(), g.cuda(), m.cuda()
+        hyper = torch.tensor([0.1, 0.9, 5e-4, 0.5, first], device="cuda")
+        check(lib.sv_sgd_step(ptr(pd), ptr(gd), ptr(md), ptr(hyper), n, sv.stream()))
+        assert rel_rms(pd[:n], want_p[:n]) < 1e-6 and rel_rms(md[:n], mm[:n]) < 1e-6
+        assert float(gd[:n].abs().max()) == 0.0 and float(gd[n]) == float(g[n])
+
+
+def test_linear_kernels_match_torch(sv):
+    from shotvae_b200._abi import lib, check, ptr
+    torch.manual_seed(29)
+    for B, N, K, kn in ((32, 128, 128, 0), (24, 10, 640, 0), (16, 1024, 138, 1)):
+        x = torch.randn(B, K)
+        W = (torch.randn(K, N) if kn else torch.randn(N, K)).requires_grad_(True)
+        bias = torch.randn(N).requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        want = xr @ (W if kn else W.t()) + bias
+        g = torch.randn(B, N)
+        want.backward(g)
+        out = torch.empty(B, N, device="cuda")
+        st = sv.stream()
+        check(lib.sv_linear_fwd(ptr(x.cuda()), K, ptr(W.detach().cuda()), N if kn else K, kn, ptr(bias.detach().cuda()), ptr(out), None, N,
+                                None, 0, B, N, K, st))
+        assert rel_rms(out, want.detach()) < 1e-5
+        gx = torch.zeros(B, K, device="cuda")
+        check(lib.sv_linear_bwd_input(ptr(g.cuda()), None, N, ptr(W.detach().cuda()), N if kn else K, kn, ptr(gx), K, 0, B, N, K, st))
+        assert rel_rms(gx, xr.grad) < 1e-5
+        dW, db = torch.zeros_like(W.detach()).cuda(), torch.zeros(N, device="cuda")
+        check(lib.sv_linear_bwd_weight(ptr(g.cuda()), None, N, ptr(x.cuda()), K, ptr(dW), N if kn else K, kn, ptr(db), B, N, K, st))
+        assert rel_rms(dW, W.grad) < 1e-5 and rel_rms(db, bias.grad) < 1e-5
+
+
+def test_cpu_tensors_are_refused(sv):
+    from lib.criterion import VAECriterion
+    with pytest.raises(sv.ShotVaeError):
+        VAECriterion(10, 1, True)(torch.rand(2, 3, 32, 32), torch.rand(2, 3, 32, 32), torch.rand(2, 128), torch.rand(2, 128),
+                                  torch.rand(2, 10))
