@@ -184,15 +184,15 @@ __global__ void __launch_bounds__(256) igemm_fprop_mma_kernel(const IgemmParams 
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += rr[j];
     }
-    if (p.out != nullptr) {
-      const bf16x8 o = pack8(v);
-      *reinterpret_cast<bf16x8*>(p.out + pix * p.N + nbase) = o;
-      unpack8(o, v);  // statistics of the values actually stored
-    }
     if (p.outf != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (nbase + j < p.n_valid) p.outf[pix * p.n_valid + nbase + j] = v[j];
+    }
+    if (p.out != nullptr) {
+      const bf16x8 o = pack8(v);
+      *reinterpret_cast<bf16x8*>(p.out + pix * p.N + nbase) = o;
+      unpack8(o, v);  // statistics of the values actually stored
     }
     if (p.stats != nullptr) {
       if (one_group) {

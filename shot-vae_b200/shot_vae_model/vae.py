@@ -40,7 +40,7 @@ class Sample(nn.Module):
 
 class _VAEFunction(torch.autograd.Function):
     @staticmethod
-    def forward(fctx, anchor, model, x, mixup, disc_label, disc_pseudo_label, mixup_lam):
+    def forward(fctx, anchor, model, x, mixup, disc_label, disc_pseudo_label, mixup_lam, grad_enabled):
         net = model._net
         B = x.size(0)
         ctx = model._acquire_ctx(B)
@@ -60,9 +60,9 @@ class _VAEFunction(torch.autograd.Function):
             label = disc_label.to(dev, torch.int64).contiguous()
             if mixup:
                 lam_dev = torch.tensor([float(mixup_lam), float(1 - mixup_lam)], dtype=torch.float32).to(dev)
-                lat = net.sample_fwd(ctx, 0, 1, eps, label=label, label_mix=disc_pseudo_label.to(dev, torch.int64).contiguous(),
-                                     lam_dev=lam_dev)
-                ctx.keep = (label, lam_dev)
+                label_mix = disc_pseudo_label.to(dev, torch.int64).contiguous()
+                lat = net.sample_fwd(ctx, 0, 1, eps, label=label, label_mix=label_mix, lam_dev=lam_dev)
+                ctx.keep = (label, label_mix, lam_dev)
             else:
                 lat = net.sample_fwd(ctx, 0, 0, eps, label=label)
                 ctx.keep = (label,)
@@ -77,7 +77,7 @@ class _VAEFunction(torch.autograd.Function):
             net.bn_running_update([(ctx, 0)])
         fctx.model, fctx.pctx = model, ctx
         fctx.set_materialize_grads(False)
-        needs_bwd = torch.is_grad_enabled() and anchor.requires_grad
+        needs_bwd = grad_enabled and anchor.requires_grad   # (grad mode is always off inside Function.forward)
         outs = (rec, mu.clone(), ls.clone(), la.clone())
         if not needs_bwd:
             model._release_ctx(ctx)
@@ -103,14 +103,15 @@ class _VAEFunction(torch.autograd.Function):
         if g_rec is not None:
             cp = pad16(net.in_ch)
             g_img = ctx.t("g.rec", (B, 32, 32, cp))
-            check(lib.sv_pack_image(ptr(g_rec.contiguous().float()), ptr(g_img), B, net.in_ch, 32 * 32, cp, st))
+            g_rec = g_rec.contiguous().float()      # (held in a variable: ptr() of a temporary would dangle)
+            check(lib.sv_pack_image(ptr(g_rec), ptr(g_img), B, net.in_ch, 32 * 32, cp, st))
             g_lat = net.decoder_bwd(ctx, g_img)
             net.sample_bwd(ctx, 0, g_lat, gm, gl, ga, accumulate=1)
         g_feat = net.heads_bwd(ctx, gm, gl, ga)
         net.encoder_bwd(ctx, g_feat)
         model._release_ctx(ctx)
         fctx.pctx = None
-        return (None,) * 7
+        return (None,) * 8
 
 
 class VariationalAutoEncoder(nn.Module):
@@ -215,4 +216,5 @@ class VariationalAutoEncoder(nn.Module):
         if not self.training:
             raise NotImplementedError("eval-mode (running-statistics) forward is outside the training hot path")
         self._ensure_bound()
-        return _VAEFunction.apply(self._first, self, input_img, mixup, disc_label, disc_pseudo_label, mixup_lam)
+        return _VAEFunction.apply(self._first, self, input_img, mixup, disc_label, disc_pseudo_label, mixup_lam,
+                                  torch.is_grad_enabled())

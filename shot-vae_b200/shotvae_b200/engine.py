@@ -1,0 +1,297 @@
+"""Fused training-step engine: the loop body of main_shot_vae.train (:281-366) / main_M2_vae.train
+(:258-307) as one explicit launch sequence on libshotvae -- no autograd, no per-op Python in the
+steady state (the sequence is captured into a CUDA graph and replayed).
+
+B200-first restructuring of the reference step (results unchanged):
+  * the four network passes are batched two by two: [P1 labelled | P3 unlabelled] and then
+    [P2 label-smoothed | P4 mixed-up] run as G=2 pass groups through the same launches (BatchNorm
+    statistics stay per pass), halving the launch count and doubling the tiles per launch;
+  * both backwards accumulate straight into the flat gradient arena; loss scalars, their signs and
+    every schedule coefficient live in device memory, so nothing synchronises with the host;
+  * SGD (momentum + weight decay) is one kernel over the flat arena; BatchNorm running statistics are
+    updated once per step in the reference's pass order P1, P2, P3, P4;
+  * with world_size > 1 the gradient arena is all-reduced in buckets on a side stream while the
+    remaining backward runs (ddp.py).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import lib, check, ptr
+from .plan import Ctx, pad16
+
+TERM_NAMES = ("rec_l", "klc_l", "kld_l", "rec_u", "klc_u", "kld_u", "disc_post_l", "cont_post_l", "disc_post_u",
+              "cont_post_u", "kl_inference")
+
+
+def alpha_schedule(epoch, max_epoch, alpha_max):
+    """main_shot_vae.py:518-520"""
+    return alpha_max * math.exp(-5 * (1 - min(1, epoch / max_epoch)) ** 2)
+
+
+def default_hyper(dataset="Cifar10", m2=False):
+    """argparse defaults of main_shot_vae.py:30-106 with the per-dataset overrides (:139,:161-163;
+    main_M2_vae.py:123,146-147)"""
+    h = dict(epochs=600, akb=200, aew=400, apw=200, ewm=1e-3, kbmc=1e-3, kbmd=1e-3, pwm=1.0, wrd=1.0, wmf=0.4, cmi=0.0,
+             dmi=2.3, epsilon=0.1, om=False, lr=0.1, momentum=0.9, wd=5e-4, x_sigma=1.0, br=True)
+    if dataset == "Cifar100":
+        h.update(akb=150, apw=400, dmi=4.6)
+    if m2:
+        h.update(cmi=200.0 if dataset == "Cifar10" else 1280.0)
+    return h
+
+
+class TrainStep:
+    def __init__(self, model, batch, hyper=None, m2=False, use_graph=True, device_noise=True, skip_dead_decoders=False,
+                 reducer=None):
+        model._ensure_bound()
+        self.model, self.net = model, model._net
+        net = self.net
+        self.B, self.m2 = int(batch), bool(m2)
+        self.h = dict(default_hyper(m2=m2) if hyper is None else hyper)
+        self.use_graph, self.device_noise = use_graph, device_noise
+        self.skip_dead_decoders = skip_dead_decoders
+        self.reducer = reducer
+        dev, B, nd, D = net.device, self.B, net.nd, net.ldc
+        self.dev = dev
+        f32, i64 = torch.float32, torch.int64
+        z = lambda *s, dtype=f32: torch.zeros(*s, dtype=dtype, device=dev)
+        # static device inputs
+        self.img_l, self.img_u = z(B, net.in_ch, 32, 32), z(B, net.in_ch, 32, 32)
+        self.label_l, self.label_u = z(B, dtype=i64), z(B, dtype=i64)
+        self.lam = z(4)                                  # {lam_l, 1-lam_l, lam_u, 1-lam_u}
+        self.idx_l, self.idx_u, self.s_lab = z(B, dtype=i64), z(B, dtype=i64), z(B, dtype=i64)
+        self.eps, self.unif = z(4, B, D), z(2, B, nd)
+        # device-resident scalars
+        self.coef = z(16)
+        self.sgd_hyper = z(8)
+        self.terms = z(16)
+        # mixup targets
+        self.s_mu, self.s_sig, self.s_alpha = z(B, D), z(B, D), z(B, nd)
+        self.m_mu, self.m_sig, self.m_alpha = z(B, D), z(B, D), z(B, nd)
+        self.ctxA = Ctx(net, 2, B)
+        self.ctxB = None if m2 else Ctx(net, 2, B)
+        self.graph = None
+        self.launches_per_step = None
+        self._epoch = None
+        self._steps_done = 0
+        # pinned host staging for the end-to-end path
+        pin = lambda *s, dtype=f32: torch.zeros(*s, dtype=dtype).pin_memory()
+        self.h_img_l, self.h_img_u = pin(B, net.in_ch, 32, 32), pin(B, net.in_ch, 32, 32)
+        self.h_label_l, self.h_label_u = pin(B, dtype=i64), pin(B, dtype=i64)
+        self.h_lam, self.h_idx = pin(4), pin(3, B, dtype=i64)
+        self.h_terms = pin(16)
+        self.set_epoch(0)
+        self.set_lr(self.h["lr"])
+        net.zero_grads()
+
+    # ---- schedules ---------------------------------------------------------------------------
+    def set_epoch(self, epoch):
+        h = self.h
+        cmi, dmi = alpha_schedule(epoch, h["akb"], h["cmi"]), alpha_schedule(epoch, h["akb"], h["dmi"])
+        ew = alpha_schedule(epoch, h["aew"], h["ewm"])
+        kbc, kbd = alpha_schedule(epoch, h["akb"], h["kbmc"]), alpha_schedule(epoch, h["akb"], h["kbmd"])
+        pwm = alpha_schedule(epoch, h["apw"], h["pwm"])
+        ucw = alpha_schedule(epoch, round(h["wmf"] * h["epochs"]), h["wrd"])
+        self.sched = dict(cmi=cmi, dmi=dmi, ew=ew, kbc=kbc, kbd=kbd, pwm=pwm, ucw=ucw)
+        c = torch.zeros(16, dtype=torch.float32)
+        c[0] = ew
+        c[1:6] = torch.tensor([ew, kbc, cmi, kbd, dmi])
+        c[6:8] = torch.tensor([1.0, 0.0 if self.m2 else ew * kbc * pwm])
+        c[8:10] = torch.tensor([ucw, ew * kbc * pwm])
+        self.coef.copy_(c)
+        self._epoch = epoch
+
+    def set_lr(self, lr):
+        world = 1 if self.reducer is None else self.reducer.world
+        hy = torch.tensor([lr, self.h["momentum"], self.h["wd"], 1.0 / world, 1.0 if self._steps_done == 0 else 0.0, 0, 0, 0],
+                          dtype=torch.float32)
+        self.sgd_hyper.copy_(hy)
+        self._lr = lr
+
+    # ---- host-side draws (reference: np.random.beta / torch.randperm on the host) -----------------
+    def draw_host(self):
+        """lambda and pairing draws in the reference's order: beta(eps,eps), randperm (label smoothing),
+        beta(2,2), randperm (mixup)."""
+        B = self.B
+        if self.m2:
+            return None
+        lam_l = float(np.random.beta(self.h["epsilon"], self.h["epsilon"])) if self.h["epsilon"] > 0 else 1.0
+        idx_l = torch.randperm(B)
+        lam_u = float(np.random.beta(2.0, 2.0))
+        idx_u = torch.arange(B) if self.h["om"] else torch.randperm(B)
+        return lam_l, idx_l, lam_u, idx_u
+
+    def stage_draws(self, draws, label_l_host):
+        if draws is None:
+            return
+        lam_l, idx_l, lam_u, idx_u = draws
+        self.h_lam.copy_(torch.tensor([lam_l, 1 - lam_l, lam_u, 1 - lam_u], dtype=torch.float64).float())
+        self.h_idx[0].copy_(idx_l)
+        self.h_idx[1].copy_(idx_u)
+        self.h_idx[2].copy_(label_l_host[idx_l])
+        self.lam.copy_(self.h_lam, non_blocking=True)
+        self.idx_l.copy_(self.h_idx[0], non_blocking=True)
+        if not self.h["om"]:
+            self.idx_u.copy_(self.h_idx[1], non_blocking=True)
+        self.s_lab.copy_(self.h_idx[2], non_blocking=True)
+
+    # ---- the launch sequence -----------------------------------------------------------------------
+    def _losses_first(self, ctx, rec):
+        """ELBO terms + gradients for the [labelled | unlabelled] group pair"""
+        net, B, st = self.net, self.B, _abi.stream()
+        nd, D, ch = net.nd, net.ldc, net.in_ch
+        mu, ls, la = ctx.bufs["mu"], ctx.bufs["ls"], ctx.bufs["la"]
+        cp = pad16(ch)
+        g_rec = ctx.t("g.rec", (2 * B, 32, 32, cp))
+        g_mu, g_ls, g_la = ctx.t("g.mu", (2 * B, D), torch.float32), ctx.t("g.ls", (2 * B, D), torch.float32), \
+            ctx.t("g.la", (2 * B, nd), torch.float32)
+        bce = 1 if self.h["br"] else 0
+        for g, img in ((0, self.img_l), (1, self.img_u)):
+            r = slice(g * B, (g + 1) * B)
+            t = self.terms[3 * g:]
+            check(lib.sv_elbo_rec_fwd_bwd(ptr(img), ptr(rec[r]), 1, B, ch, 32 * 32, bce, float(self.h["x_sigma"]), ptr(self.coef),
+                                          ptr(t), ptr(g_rec[r]), cp, None, st))
+            check(lib.sv_elbo_kl_fwd(ptr(mu[r]), ptr(ls[r]), ptr(la[r]), B, D, nd, ptr(t), st))
+            check(lib.sv_elbo_kl_bwd(ptr(mu[r]), ptr(ls[r]), ptr(la[r]), ptr(t), ptr(self.coef[1:]), 0, B, D, nd, ptr(g_mu[r]),
+                                     ptr(g_ls[r]), ptr(g_la[r]), 0, st))
+        check(lib.sv_inference_kl(ptr(la[B:]), ptr(self.label_u), B, nd, ptr(self.terms[10:]), st))
+        return g_rec, g_mu, g_ls, g_la
+
+    def _noise(self):
+        if self.device_noise:
+            self.eps.normal_()
+            self.unif.uniform_()
+
+    def _sequence(self):
+        net, B, st = self.net, self.B, _abi.stream()
+        nd, D, ch = net.nd, net.ldc, net.in_ch
+        cp = pad16(ch)
+        A, Bc = self.ctxA, self.ctxB
+        A.reset()
+        self.terms.zero_()
+        net.pack_weights()
+        self._noise()
+        # ---- forward of [P1 | P3]
+        xA = A.t("x_img", (2 * B, 32, 32, cp))
+        check(lib.sv_pack_image(ptr(self.img_l), ptr(xA[:B]), B, ch, 32 * 32, cp, st))
+        check(lib.sv_pack_image(ptr(self.img_u), ptr(xA[B:]), B, ch, 32 * 32, cp, st))
+        feat = net.encoder_fwd(A, xA)
+        mu, ls, la = net.heads_fwd(A, feat)
+        net.sample_fwd(A, 0, 0, self.eps[0], label=self.label_l)
+        lat = net.sample_fwd(A, 1, 2, self.eps[2], unif=self.unif[0])
+        rec = net.decoder_fwd(A, lat)
+        g_rec, g_mu, g_ls, g_la = self._losses_first(A, rec)
+        if self.m2:
+            # supervised cross-entropy on the labelled half (main_M2_vae.py:276-277)
+            check(lib.sv_posterior_fwd_bwd(ptr(la[:B]), None, ptr(self.label_l), None, None, None, None, None, None,
+                                           ptr(self.coef[6:]), B, D, nd, ptr(self.terms[6:]), ptr(g_la[:B]), None, None, 1, st))
+        else:
+            Bc.reset()
+            # ---- label smoothing (P1 -> P2 inputs) and optimal-interpolation mixup (P3 -> P4 inputs)
+            xB = Bc.t("x_img", (2 * B, 32, 32, cp))
+            check(lib.sv_mixup_lerp(ptr(self.img_l), ptr(mu[:B]), ptr(ls[:B]), ptr(la[:B]), ptr(self.idx_l), ptr(self.lam), B, ch,
+                                    32 * 32, D, nd, None, ptr(xB[:B]), cp, ptr(self.s_mu), ptr(self.s_sig), ptr(self.s_alpha), st))
+            if self.h["om"]:
+                check(lib.sv_pairwise_kl_second_nearest(ptr(mu[B:]), ptr(ls[B:]), B, D, ptr(self.idx_u), None, st))
+            check(lib.sv_mixup_lerp(ptr(self.img_u), ptr(mu[B:]), ptr(ls[B:]), ptr(la[B:]), ptr(self.idx_u), ptr(self.lam[2:]), B, ch,
+                                    32 * 32, D, nd, None, ptr(xB[B:]), cp, ptr(self.m_mu), ptr(self.m_sig), ptr(self.m_alpha), st))
+            # ---- forward of [P2 | P4]
+            featB = net.encoder_fwd(Bc, xB)
+            mu2, ls2, la2 = net.heads_fwd(Bc, featB)
+            if not self.skip_dead_decoders:
+                # the reconstructions of P2/P4 are discarded by the reference (main_shot_vae.py:311,356) but
+                # their decoder forwards still update the BatchNorm running statistics
+                net.sample_fwd(Bc, 0, 1, self.eps[1], label=self.label_l, label_mix=self.s_lab, lam_dev=self.lam)
+                latB = net.sample_fwd(Bc, 1, 2, self.eps[3], unif=self.unif[1])
+                net.decoder_fwd(Bc, latB)
+            g_mu2, g_ls2, g_la2 = Bc.t("g.mu", (2 * B, D), torch.float32), Bc.t("g.ls", (2 * B, D), torch.float32), \
+                Bc.t("g.la", (2 * B, nd), torch.float32)
+            check(lib.sv_posterior_fwd_bwd(ptr(la2[:B]), None, ptr(self.label_l), ptr(self.s_lab), ptr(self.lam), ptr(mu2[:B]),
+                                           ptr(ls2[:B]), ptr(self.s_mu), ptr(self.s_sig), ptr(self.coef[6:]), B, D, nd,
+                                           ptr(self.terms[6:]), ptr(g_la2[:B]), ptr(g_mu2[:B]), ptr(g_ls2[:B]), 0, st))
+            check(lib.sv_posterior_fwd_bwd(ptr(la2[B:]), ptr(self.m_alpha), None, None, None, ptr(mu2[B:]), ptr(ls2[B:]),
+                                           ptr(self.m_mu), ptr(self.m_sig), ptr(self.coef[8:]), B, D, nd, ptr(self.terms[8:]),
+                                           ptr(g_la2[B:]), ptr(g_mu2[B:]), ptr(g_ls2[B:]), 0, st))
+            # ---- backward of [P2 | P4]: heads + encoder only
+            net.encoder_bwd(Bc, net.heads_bwd(Bc, g_mu2, g_ls2, g_la2))
+        # ---- backward of [P1 | P3]
+        g_lat = net.decoder_bwd(A, g_rec)
+        if self.reducer is not None:
+            self.reducer.bucket_ready("decoder")
+        net.sample_bwd(A, 0, g_lat, g_mu, g_ls, None, accumulate=1)
+        net.sample_bwd(A, 1, g_lat, g_mu, g_ls, g_la, accumulate=1)
+        net.encoder_bwd(A, net.heads_bwd(A, g_mu, g_ls, g_la))
+        if self.reducer is not None:
+            self.reducer.bucket_ready("encoder")
+            self.reducer.wait_all()
+        # ---- optimizer + BatchNorm running statistics
+        check(lib.sv_sgd_step(ptr(net.params), ptr(net.grads), ptr(net.momentum), ptr(self.sgd_hyper), net.n_params, st))
+        if self.m2:
+            net.bn_running_update([(A, 0), (A, 1)])
+        elif self.skip_dead_decoders:
+            net.bn_running_update([(A, 0), (Bc, 0), (A, 1), (Bc, 1)])
+        else:
+            net.bn_running_update([(A, 0), (Bc, 0), (A, 1), (Bc, 1)])
+
+    # ---- public API --------------------------------------------------------------------------------
+    def run_resident(self):
+        """one optimizer step on the inputs currently resident in the static device buffers"""
+        if self._steps_done == 1:
+            self.sgd_hyper[4:5].zero_()       # momentum buffer is initialised; torch semantics from now on
+        if not self.use_graph:
+            self._sequence()
+        elif self.graph is None and self._steps_done >= 2:
+            n0 = _abi.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._sequence()
+            self.launches_per_step = _abi.launch_count() - n0
+            self.graph = g
+            g.replay()
+        elif self.graph is not None:
+            self.graph.replay()
+        else:
+            n0 = _abi.launch_count()
+            self._sequence()              # eager warm-up steps allocate every buffer
+            self.launches_per_step = _abi.launch_count() - n0
+        self._steps_done += 1
+
+    def load_inputs(self, image_l, label_l, image_u, label_u, draws="auto"):
+        """host -> device copy of one (labelled, unlabelled) batch pair through pinned staging buffers,
+        plus the host RNG draws of this step"""
+        self.h_img_l.copy_(image_l); self.h_img_u.copy_(image_u)
+        self.h_label_l.copy_(label_l); self.h_label_u.copy_(label_u)
+        self.img_l.copy_(self.h_img_l, non_blocking=True)
+        self.img_u.copy_(self.h_img_u, non_blocking=True)
+        self.label_l.copy_(self.h_label_l, non_blocking=True)
+        self.label_u.copy_(self.h_label_u, non_blocking=True)
+        self.stage_draws(self.draw_host() if draws == "auto" else draws, self.h_label_l)
+
+    def h2d_bytes(self):
+        n = self.h_img_l.numel() * 4 * 2 + self.B * 8 * 2
+        if not self.m2:
+            n += 16 + self.B * 8 * (2 if self.h["om"] else 3)
+        return n
+
+    def step(self, image_l, label_l, image_u, label_u, draws="auto"):
+        """end-to-end call: host batch in, loss terms (host floats) out"""
+        self.load_inputs(image_l, label_l, image_u, label_u, draws)
+        self.run_resident()
+        return self.read_terms()
+
+    def read_terms(self):
+        self.h_terms.copy_(self.terms, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        t = {k: float(self.h_terms[i]) for i, k in enumerate(TERM_NAMES)}
+        s = self.sched
+        for sfx in ("l", "u"):
+            t["prior_" + sfx] = s["kbc"] * abs(t["klc_" + sfx] - s["cmi"]) + s["kbd"] * abs(t["kld_" + sfx] - s["dmi"])
+        return t
+
+    def set_noise(self, eps4, unif2):
+        """parity mode: host-drawn noise in pass order (P1, P2, P3, P4) / (P3, P4)"""
+        self.eps.copy_(eps4)
+        self.unif.copy_(unif2)

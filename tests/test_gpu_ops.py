@@ -210,7 +210,8 @@ def test_bn_act_forward_backward(sv, Cc, HW, B, G, slope):
     yd = y.to(torch.bfloat16).cuda()
     stats = torch.stack([torch.stack([y[g * B:(g + 1) * B].sum(dim=(0, 1)), (y[g * B:(g + 1) * B] ** 2).sum(dim=(0, 1))]) for g in range(G)]).cuda()
     mean, var, scale, shift = (torch.empty(G, Cc, device="cuda") for _ in range(4))
-    check(lib.sv_bn_finalize(ptr(stats), ptr(gamma.cuda()), ptr(beta.cuda()), float(B * HW), 1e-5, G, Cc, Cc, ptr(mean), ptr(var),
+    gamma_d, beta_d, addend_d = gamma.cuda(), beta.cuda(), addend.to(torch.bfloat16).cuda()   # keep alive: ptr() of a temporary dangles
+    check(lib.sv_bn_finalize(ptr(stats), ptr(gamma_d), ptr(beta_d), float(B * HW), 1e-5, G, Cc, Cc, ptr(mean), ptr(var),
                              ptr(scale), ptr(shift), st))
     a = torch.empty_like(yd)
     check(lib.sv_bn_act_fwd(ptr(yd), ptr(a), ptr(scale), ptr(shift), slope, B * HW, G, Cc, st))
@@ -227,7 +228,7 @@ def test_bn_act_forward_backward(sv, Cc, HW, B, G, slope):
     term[0].dgamma, term[0].dbeta, term[0].grad_gamma, term[0].grad_beta = ptr(dg), ptr(db), ptr(gg), ptr(gb)
     term[0].slope, term[0].c_real = slope, Cc
     gy = torch.empty_like(yd)
-    check(lib.sv_bn_bwd_apply(term, 1, ptr(yd), ptr(addend.to(torch.bfloat16).cuda()), ptr(gy), 1e-5, B * HW, HW, G, Cc, st))
+    check(lib.sv_bn_bwd_apply(term, 1, ptr(yd), ptr(addend_d), ptr(gy), 1e-5, B * HW, HW, G, Cc, st))
     assert rel_rms(gy.float().cpu().view(-1, Cc), torch.cat(gys)) < 6e-3
     assert rel_rms(gg.cpu(), gam_ref.grad) < 1e-3 and rel_rms(gb.cpu(), bet_ref.grad) < 1e-3
 
@@ -283,12 +284,12 @@ def test_sample_forward_backward_matches_oracle(sv):
         lat = torch.empty(B, D + nd, device="cuda")
         lam_dev = torch.tensor([lam, 1 - lam], dtype=torch.float32).cuda()
         md, lsd, lad = mu.detach().cuda(), ls.detach().cuda(), la.detach().cuda()
-        epd, und = eps.cuda(), unif.cuda()
-        check(lib.sv_sample_fwd(ptr(md), ptr(lsd), ptr(lad), ptr(epd), ptr(und), ptr(lab.cuda()), ptr(lab2.cuda()), ptr(lam_dev), mode, T,
+        epd, und, labd, lab2d, gld = eps.cuda(), unif.cuda(), lab.cuda(), lab2.cuda(), gl.cuda()
+        check(lib.sv_sample_fwd(ptr(md), ptr(lsd), ptr(lad), ptr(epd), ptr(und), ptr(labd), ptr(lab2d), ptr(lam_dev), mode, T,
                                 B, D, nd, ptr(lat), D + nd, sv.stream()))
         assert rel_rms(lat, want.detach()) < 1e-5
         g_mu, g_ls, g_la = (torch.zeros_like(t) for t in (md, lsd, lad))
-        check(lib.sv_sample_bwd(ptr(gl.cuda()), D + nd, ptr(lsd), ptr(epd), ptr(lat), mode, T, B, D, nd, ptr(g_mu), ptr(g_ls), ptr(g_la),
+        check(lib.sv_sample_bwd(ptr(gld), D + nd, ptr(lsd), ptr(epd), ptr(lat), mode, T, B, D, nd, ptr(g_mu), ptr(g_ls), ptr(g_la),
                                 1, sv.stream()))
         assert rel_rms(g_mu, mu.grad) < 1e-5 and rel_rms(g_ls, ls.grad) < 1e-5
         if mode == 2:
@@ -355,9 +356,9 @@ def test_posterior_and_inference_kl_match_oracle(sv):
     g_la, g_mu, g_ls = torch.zeros(B, nd, device="cuda"), torch.zeros(B, D, device="cuda"), torch.zeros(B, D, device="cuda")
     coef = torch.tensor([cd, cc], device="cuda")
     lam_dev = torch.tensor([lam, 1 - lam], dtype=torch.float32).cuda()
-    check(lib.sv_posterior_fwd_bwd(ptr(la.detach().cuda()), None, ptr(la_.cuda()), ptr(lb_.cuda()), ptr(lam_dev), ptr(mu.detach().cuda()),
-                                   ptr(ls.detach().cuda()), ptr(mu_t.cuda()), ptr(sig_t.cuda()), ptr(coef), B, D, nd, ptr(terms), ptr(g_la),
-                                   ptr(g_mu), ptr(g_ls), 0, sv.stream()))
+    d = [t.detach().cuda() for t in (la, la_, lb_, mu, ls, mu_t, sig_t)]
+    check(lib.sv_posterior_fwd_bwd(ptr(d[0]), None, ptr(d[1]), ptr(d[2]), ptr(lam_dev), ptr(d[3]), ptr(d[4]), ptr(d[5]), ptr(d[6]),
+                                   ptr(coef), B, D, nd, ptr(terms), ptr(g_la), ptr(g_mu), ptr(g_ls), 0, sv.stream()))
     assert abs(float(terms[0]) - float(disc)) < 1e-5 * abs(float(disc)) and abs(float(terms[1]) - float(cont)) < 1e-5 * float(cont)
     assert rel_rms(g_la, la.grad) < 1e-5 and rel_rms(g_mu, mu.grad) < 1e-5 and rel_rms(g_ls, ls.grad) < 1e-5
     lab = torch.randint(0, nd, (B,))
@@ -365,7 +366,8 @@ def test_posterior_and_inference_kl_match_oracle(sv):
     au = torch.exp(la.detach())
     want = float(torch.sum(au * la.detach() - au * torch.log(lsu)) / B)
     out = torch.zeros(1, device="cuda")
-    check(lib.sv_inference_kl(ptr(la.detach().cuda()), ptr(lab.cuda()), B, nd, ptr(out), sv.stream()))
+    labd = lab.cuda()
+    check(lib.sv_inference_kl(ptr(d[0]), ptr(labd), B, nd, ptr(out), sv.stream()))
     assert abs(float(out) - want) < 1e-5 * abs(want)
 
 
@@ -398,14 +400,14 @@ def test_linear_kernels_match_torch(sv):
         want.backward(g)
         out = torch.empty(B, N, device="cuda")
         st = sv.stream()
-        check(lib.sv_linear_fwd(ptr(x.cuda()), K, ptr(W.detach().cuda()), N if kn else K, kn, ptr(bias.detach().cuda()), ptr(out), None, N,
-                                None, 0, B, N, K, st))
+        xd, Wd, bd, gd = x.cuda(), W.detach().cuda(), bias.detach().cuda(), g.cuda()
+        check(lib.sv_linear_fwd(ptr(xd), K, ptr(Wd), N if kn else K, kn, ptr(bd), ptr(out), None, N, None, 0, B, N, K, st))
         assert rel_rms(out, want.detach()) < 1e-5
         gx = torch.zeros(B, K, device="cuda")
-        check(lib.sv_linear_bwd_input(ptr(g.cuda()), None, N, ptr(W.detach().cuda()), N if kn else K, kn, ptr(gx), K, 0, B, N, K, st))
+        check(lib.sv_linear_bwd_input(ptr(gd), None, N, ptr(Wd), N if kn else K, kn, ptr(gx), K, 0, B, N, K, st))
         assert rel_rms(gx, xr.grad) < 1e-5
         dW, db = torch.zeros_like(W.detach()).cuda(), torch.zeros(N, device="cuda")
-        check(lib.sv_linear_bwd_weight(ptr(g.cuda()), None, N, ptr(x.cuda()), K, ptr(dW), N if kn else K, kn, ptr(db), B, N, K, st))
+        check(lib.sv_linear_bwd_weight(ptr(gd), None, N, ptr(xd), K, ptr(dW), N if kn else K, kn, ptr(db), B, N, K, st))
         assert rel_rms(dW, W.grad) < 1e-5 and rel_rms(db, bias.grad) < 1e-5
 
 
