@@ -343,6 +343,10 @@ def schedules(h, epoch):
                 ucw=alpha_schedule(epoch, round(h["wmf"] * h["epochs"]), h["wrd"]))
 
 
+def _f(t):
+    return float(t.detach()) if torch.is_tensor(t) else float(t)
+
+
 def _onehot(y, n):
     return torch.zeros(y.size(0), n).scatter_(1, y.view(-1, 1), 1)
 
@@ -398,10 +402,10 @@ def shot_step(st, encoder_name, nd, image_l, label_l, image_u, label_u, epoch, h
     elbo_u = elbo_u + s["kbc"] * s["pwm"] * cont_post_u
     loss_unsup = s["ew"] * elbo_u + s["ucw"] * disc_post_u
     loss_unsup.backward()
-    out.update(rec_l=float(rl), klc_l=float(kc), kld_l=float(kd), prior_l=float(prior_l), cont_post_l=float(cont_post_l),
-               disc_post_l=float(disc_post_l), loss_sup=float(loss_sup), lam_l=float(lam_l),
-               rec_u=float(ru), klc_u=float(kcu), kld_u=float(kdu), prior_u=float(prior_u), cont_post_u=float(cont_post_u),
-               disc_post_u=float(disc_post_u), loss_unsup=float(loss_unsup), lam_u=float(lam_u), kl_inference=kl_inf)
+    out.update(rec_l=_f(rl), klc_l=_f(kc), kld_l=_f(kd), prior_l=_f(prior_l), cont_post_l=_f(cont_post_l),
+               disc_post_l=_f(disc_post_l), loss_sup=_f(loss_sup), lam_l=_f(lam_l),
+               rec_u=_f(ru), klc_u=_f(kcu), kld_u=_f(kdu), prior_u=_f(prior_u), cont_post_u=_f(cont_post_u),
+               disc_post_u=_f(disc_post_u), loss_unsup=_f(loss_unsup), lam_u=_f(lam_u), kl_inference=kl_inf)
     if keep:
         out["tensors"] = dict(rec_l=rec_l, mu_l=mu_l, ls_l=ls_l, la_l=la_l, idx_l=idx_l, s_img=s_img, s_mu=s_mu,
                               s_sig=s_sig, s_alpha=s_alpha, s_lab=s_lab, rec2=rec2, mu2=mu2, ls2=ls2, la2=la2,
@@ -435,9 +439,9 @@ def m2_step(st, encoder_name, nd, image_l, label_l, image_u, label_u, epoch, hyp
     prior_u = s["kbc"] * torch.abs(kcu - s["cmi"]) + s["kbd"] * torch.abs(kdu - s["dmi"])
     loss_unsup = s["ew"] * (ru + prior_u)
     loss_unsup.backward()
-    out = dict(rec_l=float(rl), klc_l=float(kc), kld_l=float(kd), prior_l=float(prior_l), disc_post_l=float(disc_post_l),
-               loss_sup=float(loss_sup), rec_u=float(ru), klc_u=float(kcu), kld_u=float(kdu), prior_u=float(prior_u),
-               loss_unsup=float(loss_unsup), kl_inference=kl_inf)
+    out = dict(rec_l=_f(rl), klc_l=_f(kc), kld_l=_f(kd), prior_l=_f(prior_l), disc_post_l=_f(disc_post_l),
+               loss_sup=_f(loss_sup), rec_u=_f(ru), klc_u=_f(kcu), kld_u=_f(kdu), prior_u=_f(prior_u),
+               loss_unsup=_f(loss_unsup), kl_inference=kl_inf)
     if keep:
         out["tensors"] = dict(rec_l=rec_l, mu_l=mu_l, ls_l=ls_l, la_l=la_l, rec_u=rec_u, mu_u=mu_u, ls_u=ls_u, la_u=la_u)
     return out

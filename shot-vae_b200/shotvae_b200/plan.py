@@ -93,6 +93,20 @@ def dgrad_phase_taps(k, s, pad):
     return res
 
 
+def _valid_pairs(taps, NB, OH, OW, H, W, in_stride, exact):
+    """number of (output row, tap) pairs that contribute a MAC per (n, c): all of them for the conv
+    counting rule (padding taps count), only in-image ones for the transposed-conv
+    'effective' rule"""
+    if not exact:
+        return float(NB) * OH * OW * len(taps)
+    tot = 0
+    for _, dy, dx in taps:
+        ny = sum(1 for o in range(OH) if 0 <= o * in_stride + dy < H)
+        nx = sum(1 for o in range(OW) if 0 <= o * in_stride + dx < W)
+        tot += ny * nx
+    return float(NB) * tot
+
+
 def live_taps(taps, OH, OW, H, W, in_stride):
     """Drops taps that read outside the image for every output position (e.g. 12 of the 16 taps of the
     1x1 -> 2x2 decoder layer)."""
@@ -175,6 +189,7 @@ class Net:
         for k, v in named_buffers.items():
             self.b(k).copy_(v.detach().to(self.device))
         self.wg_ws = torch.empty(WG_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
+        self.timing = None        # bench instrumentation: list of (kind, key, flops, ev0, ev1) when enabled
         self._build_packs()
 
     # ---- views
@@ -246,7 +261,7 @@ class Net:
 
     # ---- low-level launch helpers --------------------------------------------------------------
     def _igemm(self, ctx, key, A, pack, NB, H, W, OH, OW, in_stride=1, out=None, outf=None, res=None, bias=None, stats=None,
-               out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0):
+               out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0, exact=False):
         a = ctx.args.get(key)
         if a is None:
             pk = self.packs[pack]
@@ -264,9 +279,18 @@ class Net:
         # operand pointers are refreshed on every call (callers may hand in different tensors)
         a.A, a.out_bf16, a.out_f32, a.residual, a.bias, a.stats = ptr(A), ptr(out), ptr(outf), ptr(res), ptr(bias), ptr(stats)
         a.impl = self.impl
+        if self.timing is None:
+            check(lib.sv_igemm_fprop(C.byref(a), _abi.stream()))
+            return
+        pk = self.packs[pack]
+        flops = 2.0 * pk["n_real"] * pk["c_real"] * _valid_pairs(pk["taps"], NB, OH, OW, H, W, in_stride, exact)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         check(lib.sv_igemm_fprop(C.byref(a), _abi.stream()))
+        e1.record()
+        self.timing.append(("igemm_fprop", key, flops, e0, e1))
 
-    def _wgrad(self, ctx, key, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, wname, n_real, c_real, sn, sc, st):
+    def _wgrad(self, ctx, key, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, wname, n_real, c_real, sn, sc, st, exact=False):
         ent = ctx.args.get(key)
         if ent is None:
             T = len(taps)
@@ -287,6 +311,17 @@ class Net:
         a, tidx, splits, T = ent
         a.A, a.Gr = ptr(A), ptr(Gr)
         s = _abi.stream()
+        if self.timing is not None:
+            flops = 2.0 * n_real * c_real * _valid_pairs(taps, NB, OH, OW, H, W, in_stride, exact)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            check(lib.sv_igemm_wgrad(C.byref(a), s))
+            e1.record()
+            check(lib.sv_wgrad_reduce(ptr(self.wg_ws), ptr(self.g(wname)), splits, N, Cc, T, n_real, c_real, sn, sc, st, tidx, s))
+            e2.record()
+            self.timing.append(("igemm_wgrad", key, flops, e0, e1))
+            self.timing.append(("wgrad_reduce", key, 0.0, e1, e2))
+            return
         check(lib.sv_igemm_wgrad(C.byref(a), s))
         check(lib.sv_wgrad_reduce(ptr(self.wg_ws), ptr(self.g(wname)), splits, N, Cc, T, n_real, c_real, sn, sc, st, tidx, s))
 
@@ -513,7 +548,7 @@ class Net:
                 for px in range(2):
                     self._igemm(ctx, "d%d.f%d%d" % (li + 1, py, px), a, "d%d.f%d%d" % (li + 1, py, px), NB, hin, hin, hin, hin,
                                 out=None if last else yn, outf=yn if last else None, stats=stn, out_stride=2, off=(py, px),
-                                OHf=ho, OWf=ho, n_valid=cout if last else 0)
+                                OHf=ho, OWf=ho, n_valid=cout if last else 0, exact=True)
             y, st, cin, hin = yn, stn, cout, ho
         return y
 
@@ -530,9 +565,9 @@ class Net:
             taps = self.packs["d%d.d" % (li + 1)]["taps"]
             # ConvT weight gradient: rows = coarse input pixels, Gr = a_in (N = cin), A = g_out (C = cout)
             self._wgrad(ctx, "d%d.w" % (li + 1), g, d["a"], taps, NB, ho, ho, cout_p, hin, hin, cin, 2, wname, cin, cout,
-                        cout * 16, 16, 1)
+                        cout * 16, 16, 1, exact=True)
             g_a = ctx.t("g.d%d.a" % li, (NB, hin, hin, cin))
-            self._igemm(ctx, "d%d.d" % (li + 1), g, "d%d.d" % (li + 1), NB, ho, ho, hin, hin, in_stride=2, out=g_a)
+            self._igemm(ctx, "d%d.d" % (li + 1), g, "d%d.d" % (li + 1), NB, ho, ho, hin, hin, in_stride=2, out=g_a, exact=True)
             g_y = ctx.t("g.d%d.y" % li, (NB, hin, hin, cin))
             self._bn_bwd(ctx, "d%d.bn" % li, [dict(rec=d["bn"], g_a=g_a, slope=0.0)], d["y"], None, g_y, B * hin * hin, hin * hin)
             g, cout, cout_p = g_y, cin, cin

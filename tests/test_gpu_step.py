@@ -226,3 +226,121 @@ def test_optimizer_step_and_state_roundtrip():
     g = model.feature_reconstructor.decoder[0].weight.grad
     assert g is not None and float(g.abs().max()) == 0.0          # decoder got no gradient in this backward
     assert float(model.continuous_inference.mean.fc.weight.grad.abs().max()) > 0.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused engine (shotvae_b200.engine.TrainStep): G=2 batched passes, explicit backward, fused SGD
+# ---------------------------------------------------------------------------------------------------
+def _oracle_step_with_sgd(net, nd, batch, epoch, hyper, rng_seed, data_seed, m2=False, nsteps=1):
+    from oracle import shotvae_oracle as O
+    st = O.init_state(net, nd)
+    il, ll, iu, lu = O.synthetic_batch(batch, nd, data_seed)
+    ost = O.clone_state(st)
+    torch.manual_seed(rng_seed); np.random.seed(rng_seed)
+    mom, outs, logs = {}, [], []
+    for _ in range(nsteps):
+        draws = O.LiveDraws()
+        fn = O.m2_step if m2 else O.shot_step
+        outs.append(fn(ost, net, nd, il, ll, iu, lu, epoch, hyper, draws))
+        O.sgd_step(ost, mom, hyper["lr"], hyper["momentum"], hyper["wd"])
+        logs.append(draws.log)
+    return st, ost, (il, ll, iu, lu), outs, logs
+
+
+def _feed(ts, log, m2):
+    """hand the oracle's recorded host draws to the engine (pass order P1, P2, P3, P4)"""
+    if m2:
+        eps = torch.stack([log[0][1], log[0][1], log[1][1], log[1][1]])
+        unif = torch.stack([log[2][1], log[2][1]])
+        ts.set_noise(eps.cuda(), unif.cuda())
+        return None
+    kinds = [k for k, _ in log]
+    assert kinds == ["randn", "beta", "randperm", "randn", "randn", "rand", "beta"] + (["randperm"] if len(kinds) == 10 else []) + ["randn", "rand"], kinds
+    v = [x for _, x in log]
+    if len(kinds) == 10:
+        eps, unif = torch.stack([v[0], v[3], v[4], v[8]]), torch.stack([v[5], v[9]])
+        draws = (v[1], v[2], v[6], v[7])
+    else:       # --om: no randperm for the mixup pairing
+        eps, unif = torch.stack([v[0], v[3], v[4], v[7]]), torch.stack([v[5], v[8]])
+        draws = (v[1], v[2], v[6], torch.arange(v[2].numel()))
+    ts.set_noise(eps.cuda(), unif.cuda())
+    return draws
+
+
+@pytest.mark.parametrize("net,nd,batch,epoch,om,m2,dataset", [
+    ("wideresnet-28-2", 10, 16, 100, False, False, "Cifar10"),
+    ("wideresnet-28-2", 10, 32, 400, True, False, "Cifar10"),
+    ("preactresnet18", 100, 16, 100, False, True, "Cifar100"),
+])
+def test_engine_step_matches_oracle(net, nd, batch, epoch, om, m2, dataset):
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    hyper = O.default_hyper(dataset, m2)
+    hyper["om"] = om
+    hyper["br"] = not m2
+    st, ost, (il, ll, iu, lu), outs, logs = _oracle_step_with_sgd(net, nd, batch, epoch, hyper, 5, 11, m2)
+    model = build_model(net, nd, st).train()
+    ts = TrainStep(model, batch, hyper={k: v for k, v in hyper.items() if k != "temperature"}, m2=m2, use_graph=False,
+                   device_noise=False)
+    ts.set_epoch(epoch)
+    draws = _feed(ts, logs[0], m2)
+    got = ts.step(il, ll, iu, lu, draws=draws)
+    want = outs[0]
+    tag = "engine_%s_nd%d_b%d_e%d%s%s" % (net, nd, batch, epoch, "_om" if om else "", "_m2" if m2 else "")
+    rep = {k: dict(got=got[k], want=want[k]) for k in want if k in got}
+    _report("terms_" + tag, rep)
+    for k in ("rec_l", "klc_l", "rec_u", "klc_u"):
+        assert abs(got[k] - want[k]) < 1e-3 * abs(want[k]), (k, got[k], want[k])
+    for k in ("kld_l", "kld_u"):
+        assert abs(got[k] - want[k]) < 1e-3 * max(1.0, abs(want["klc_l"]))
+    assert abs(got["kl_inference"] - want["kl_inference"]) < 5e-3 * abs(want["kl_inference"])
+    assert abs(got["disc_post_l"] - want["disc_post_l"]) < 5e-3 * abs(want["disc_post_l"])
+    if not m2:
+        assert abs(got["disc_post_u"] - want["disc_post_u"]) < 5e-3 * abs(want["disc_post_u"])
+        assert abs(got["cont_post_u"] - want["cont_post_u"]) < 2e-2 * abs(want["cont_post_u"])
+    # post-SGD parameters and BatchNorm running statistics against the oracle's step
+    sd = model.state_dict()
+    upd = {k: sd[k].float().cpu() - st[k].float() for k in O.param_names(ost)}
+    wupd = {k: ost[k].detach().float() - st[k].float() for k in O.param_names(ost)}
+    errs = grad_errors(upd, wupd)
+    _report("update_rel_l2_" + tag, errs)
+    assert errs["decoder"] < 0.15 and errs["heads"] < 0.15 and errs["encoder"] < 0.65, errs
+    rs = max(rel(sd[k], ost[k]) for k in ost if k.endswith("running_mean") or k.endswith("running_var"))
+    _report("running_stats_" + tag, rs)
+    assert rs < 3e-2
+    nb = 2 if m2 else 4
+    assert all(int(sd[k]) == nb for k in ost if k.endswith("num_batches_tracked") and "feature_extractor" in k)
+
+
+def test_engine_graph_replay_equals_eager_sequence():
+    """the CUDA-graph replay must reproduce the eagerly launched sequence bit for bit (same kernels, same
+    order, host-fed noise), over several steps including the first-step momentum initialisation"""
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    net, nd, B = "wideresnet-10-1", 10, 16
+    hyper = O.default_hyper("Cifar10")
+    st = O.init_state(net, nd)
+    il, ll, iu, lu = O.synthetic_batch(B, nd, 3)
+    res = []
+    for use_graph in (False, True):
+        model = build_model(net, nd, st).train()
+        ts = TrainStep(model, B, hyper=hyper, use_graph=use_graph, device_noise=False)
+        ts.set_epoch(200)
+        g = torch.Generator().manual_seed(1)
+        terms = []
+        for i in range(5):
+            ts.set_noise(torch.randn(4, B, 128, generator=g).cuda(), torch.rand(2, B, nd, generator=g).cuda())
+            lam_l, lam_u = 0.9 + 0.01 * i, 0.3 + 0.1 * i
+            draws = (lam_l, torch.randperm(B, generator=g), lam_u, torch.randperm(B, generator=g))
+            terms.append(ts.step(il, ll, iu, lu, draws=draws))
+        if use_graph:
+            assert ts.graph is not None and ts.launches_per_step > 200
+        res.append((terms, {k: v.clone() for k, v in model.state_dict().items()}))
+    (t0, s0), (t1, s1) = res
+    for a, b in zip(t0, t1):
+        for k in ("rec_l", "klc_l", "rec_u", "disc_post_u", "cont_post_u"):
+            assert abs(a[k] - b[k]) <= 1e-2 * abs(a[k]), (k, a[k], b[k])   # atomics: summation order differs run to run,
+            # and the difference is amplified step over step by the bf16 network
+    worst = max(rel(s1[k].float(), s0[k].float()) for k in s0 if s0[k].dtype == torch.float32)
+    _report("graph_vs_eager_state_rel", worst)
+    assert worst < 5e-2
