@@ -56,9 +56,13 @@ typedef struct {
   int32_t OHf, OWf, n_valid, group_images;
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
-  int32_t impl;         /* 0 = auto, 1 = force mma.sync kernel, 2 = force tcgen05 kernel */
+  int32_t impl;         /* 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 + per-tap TMA kernel,
+                           3 = tcgen05 halo-tile kernel (input read once, taps = shifted descriptors) */
+  int32_t w_layout;     /* layout of Wt: 0 = [T][N][C]; 1 = [T][C/8][N][8] (required by, and selects, kernel 3) */
 } sv_igemm_args;
 int sv_igemm_fprop(const sv_igemm_args* a, void* stream);
+/* 1 if kernel `impl` (1, 2, 3) can run this problem; impl = 0 returns the kernel auto mode selects */
+int sv_igemm_fprop_supports(const sv_igemm_args* a, int32_t impl);
 
 /* weight-gradient GEMM (replaces the cuDNN wgrad behind every conv / convT backward):
  * part[s][n][t*C + c] = sum over the s-th slice of rows m of  Gr[m, n] * A[gather(m, t), c]
@@ -80,9 +84,10 @@ int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits, int32_t N
                     int32_t n_real, int32_t c_real, int64_t sn, int64_t sc, int64_t st,
                     const int8_t* tap_index /* host, T entries */, void* stream);
 
-/* dst[t][n][c] (bf16) = src[n*sn + c*sc + tap_index[t]*st] for n < n_real, c < c_real else 0 */
+/* dst(t, n, c) (bf16) = src[n*sn + c*sc + tap_index[t]*st] for n < n_real, c < c_real else 0;
+ * layout 0: dst[t][n][c]; layout 1: dst[t][c/8][n][c%8] (8-channel planes, for the halo-tile kernel) */
 int sv_pack_weight(const float* src, void* dst, int32_t N, int32_t C, int32_t T, int32_t n_real, int32_t c_real,
-                   int64_t sn, int64_t sc, int64_t st, const int8_t* tap_index /* host */, void* stream);
+                   int64_t sn, int64_t sc, int64_t st, const int8_t* tap_index /* host */, int32_t layout, void* stream);
 /* fp32 NCHW [NB, c_real, H, W] -> bf16 NHWC [NB, H, W, C] (zero padded channels) */
 int sv_pack_image(const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream);
 /* fp32 NHWC [NB, HW, c_real] -> fp32 NCHW [NB, c_real, HW] */
@@ -201,6 +206,10 @@ int sv_pairwise_kl_second_nearest(const float* mu, const float* ls, int32_t B, i
  * g = grad*grad_scale + wd*p ; m = first ? g : mom*m + g ; p -= lr*m ; grad = 0.  hyper (device) =
  * {lr, momentum, wd, grad_scale, first_step_flag}. */
 int sv_sgd_step(float* param, float* grad, float* momentum_buf, const float* hyper, int64_t n, void* stream);
+
+/* debugging aid: per-tile clock64 stamps of CTA 0 of the last halo-kernel launch run with
+ * SHOTVAE_HALO_TRACE=1 ([role: producer, mma, mma-acc-wait, epilogue][tile < 64][begin, end]) */
+int sv_debug_halo_trace(long long* host_out);
 
 /* struct sizes, so the ctypes mirror can be checked at load time */
 int sv_sizeof_igemm_args(void);

@@ -1,5 +1,6 @@
 // C-ABI plumbing: error state, launch accounting, argument validation, kernel selection.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include "common.cuh"
 #include "igemm.h"
@@ -40,14 +41,13 @@ int sv_has_tcgen05(void) { return 0; }
 int sv_has_tcgen05(void) { return 1; }
 #endif
 
-int sv_igemm_fprop(const sv_igemm_args* a, void* stream) {
+static int fill_params(const sv_igemm_args* a, IgemmParams& p) {
   SV_REQUIRE(a && a->A && a->Wt, "sv_igemm_fprop: null operand");
   SV_REQUIRE(a->C % 16 == 0 && a->N % 16 == 0, "sv_igemm_fprop: C (%d) and N (%d) must be multiples of 16", a->C, a->N);
   SV_REQUIRE(a->T >= 1 && a->T <= SV_MAX_TAPS, "sv_igemm_fprop: T=%d out of range", a->T);
   SV_REQUIRE(a->NB > 0 && a->OH > 0 && a->OW > 0 && a->group_images > 0, "sv_igemm_fprop: bad geometry");
   SV_REQUIRE(a->out_bf16 || a->out_f32, "sv_igemm_fprop: no output");
   SV_REQUIRE((long long)a->NB * a->OH * a->OW < (1ll << 31), "sv_igemm_fprop: too many rows");
-  IgemmParams p;
   p.A = (const bf16*)a->A; p.Wt = (const bf16*)a->Wt; p.out = (bf16*)a->out_bf16; p.outf = a->out_f32;
   p.res = (const bf16*)a->residual; p.bias = a->bias; p.stats = a->stats;
   p.NB = a->NB; p.H = a->H; p.W = a->W; p.C = a->C; p.OH = a->OH; p.OW = a->OW; p.N = a->N; p.T = a->T;
@@ -55,17 +55,60 @@ int sv_igemm_fprop(const sv_igemm_args* a, void* stream) {
   p.OHf = a->OHf; p.OWf = a->OWf; p.n_valid = a->n_valid; p.group_images = a->group_images;
   p.M = a->NB * a->OH * a->OW;
   p.rows_per_group = a->group_images * a->OH * a->OW;
+  p.w_layout = a->w_layout;
   memcpy(p.dy, a->dy, SV_MAX_TAPS); memcpy(p.dx, a->dx, SV_MAX_TAPS);
-  cudaStream_t st = (cudaStream_t)stream;
+  return SV_OK;
+}
+
+// SHOTVAE_IGEMM=mma forces the mma.sync kernels in auto mode (debug switch, not a dispatch layer)
+static bool auto_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SHOTVAE_IGEMM");
+    v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int select_impl(const IgemmParams& p) {
 #ifndef SV_NO_TCGEN05
-  if (a->impl == 2) {
-    SV_REQUIRE(igemm_fprop_tc_supported(p), "sv_igemm_fprop: shape not supported by the tcgen05 kernel");
+  if (p.w_layout == 1) return 3;
+  if (auto_tc_enabled() && igemm_fprop_tc_supported(p)) return 2;
+#endif
+  return 1;
+}
+
+int sv_igemm_fprop_supports(const sv_igemm_args* a, int32_t impl) {
+  IgemmParams p;
+  if (fill_params(a, p) != SV_OK) return 0;
+  if (impl == 0) return select_impl(p);
+  if (impl == 1) return p.w_layout == 0 ? 1 : 0;
+#ifndef SV_NO_TCGEN05
+  if (impl == 2) return igemm_fprop_tc_supported(p) ? 1 : 0;
+  if (impl == 3) return igemm_fprop_halo_supported(p) ? 1 : 0;
+#endif
+  return 0;
+}
+
+int sv_igemm_fprop(const sv_igemm_args* a, void* stream) {
+  IgemmParams p;
+  int rc = fill_params(a, p);
+  if (rc != SV_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int impl = a->impl;
+  if (impl == 0) impl = select_impl(p);
+#ifndef SV_NO_TCGEN05
+  if (impl == 2) {
+    SV_REQUIRE(igemm_fprop_tc_supported(p), "sv_igemm_fprop: shape not supported by the tcgen05 per-tap kernel");
     return igemm_fprop_tc(p, st);
   }
-  if (a->impl == 0 && igemm_fprop_tc_supported(p)) return igemm_fprop_tc(p, st);
-#else
-  SV_REQUIRE(a->impl != 2, "sv_igemm_fprop: built without tcgen05");
+  if (impl == 3) {
+    SV_REQUIRE(igemm_fprop_halo_supported(p), "sv_igemm_fprop: shape not supported by the tcgen05 halo kernel");
+    return igemm_fprop_halo(p, st);
+  }
 #endif
+  SV_REQUIRE(impl == 1, "sv_igemm_fprop: unknown impl %d", impl);
+  SV_REQUIRE(p.w_layout == 0, "sv_igemm_fprop: plane-interleaved weights are only consumed by the halo kernel");
   return igemm_fprop_mma(p, st);
 }
 

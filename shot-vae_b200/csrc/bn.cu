@@ -15,13 +15,13 @@ struct ColShape {
   long long slab_rows;
 };
 
-static ColShape col_shape(long long rows_per_group, int G, int C) {
+static ColShape col_shape(long long rows_per_group, int G, int C, int blocks_per_sm = 8) {
   ColShape s;
   s.cpr = C / 8;
   s.rl = 256 / s.cpr;
   if (s.rl < 1) s.rl = 1;
   s.threads = s.cpr * s.rl;
-  long long want = (148ll * 8) / (G > 0 ? G : 1);
+  long long want = (148ll * blocks_per_sm) / (G > 0 ? G : 1);
   if (want < 1) want = 1;
   long long by_rows = ceil_div_ll(rows_per_group, (long long)s.rl * 4);
   s.slabs = (int)(by_rows < want ? by_rows : want);
@@ -129,24 +129,46 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
   const float inv_hw = 1.f / (float)HW;
   const long long r0 = (long long)blockIdx.x * slab_rows;
   const long long r1 = min(r0 + slab_rows, rows_per_group);
-  for (long long r = r0 + rl; r < r1; r += nrl) {
-    const size_t row = (size_t)g * rows_per_group + r;
-    const size_t off = row * C + chunk * 8;
-    float gv[8], yv[8];
-    if (FEAT) {
-      const size_t nb = row / HW;
+  constexpr int U = 4;      // rows in flight per thread (memory-level parallelism)
+  for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
+    bf16x8 gq[U], yq[U];
+    float gf[U][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) gv[j] = g_feat[nb * C + chunk * 8 + j] * inv_hw;
-    } else {
-      unpack8(*reinterpret_cast<const bf16x8*>(g_a + off), gv);
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * nrl;
+      if (r < r1) {
+        const size_t row = (size_t)g * rows_per_group + r;
+        const size_t off = row * C + chunk * 8;
+        if (FEAT) {
+          const size_t nb = row / HW;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gf[u][j] = g_feat[nb * C + chunk * 8 + j] * inv_hw;
+        } else {
+          gq[u] = *reinterpret_cast<const bf16x8*>(g_a + off);
+        }
+        yq[u] = *reinterpret_cast<const bf16x8*>(y + off);
+      }
     }
-    unpack8(*reinterpret_cast<const bf16x8*>(y + off), yv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float pre = fmaf(yv[j], sc[j], sh[j]);
-      const float gp = pre > 0.f ? gv[j] : slope * gv[j];
-      ab[j] += gp;
-      ag[j] += gp * (yv[j] - mu[j]) * rs[j];
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * nrl;
+      if (r < r1) {
+        float gv[8], yv[8];
+        if (FEAT) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gv[j] = gf[u][j];
+        } else {
+          unpack8(gq[u], gv);
+        }
+        unpack8(yq[u], yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pre = fmaf(yv[j], sc[j], sh[j]);
+          const float gp = pre > 0.f ? gv[j] : slope * gv[j];
+          ab[j] += gp;
+          ag[j] += gp * (yv[j] - mu[j]) * rs[j];
+        }
+      }
     }
   }
   __syncthreads();
@@ -350,7 +372,7 @@ int sv_bn_bwd_reduce(const void* g_a, const float* g_feat, const void* y, const 
                      int32_t G, int32_t C, float* dgamma, float* dbeta, void* stream) {
   SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_bwd_reduce: unsupported C=%d", C);
   SV_REQUIRE((g_a != nullptr) != (g_feat != nullptr), "sv_bn_bwd_reduce: exactly one of g_a / g_feat");
-  const ColShape s = col_shape(rows_per_group, G, C);
+  const ColShape s = col_shape(rows_per_group, G, C, 2);   // few blocks: each ends with 2*C global atomics
   const size_t smem = 2 * (size_t)C * sizeof(float);
   if (g_feat)
     bn_bwd_reduce_kernel<true><<<dim3(s.slabs, G), s.threads, smem, (cudaStream_t)stream>>>(

@@ -17,6 +17,7 @@ struct IgemmParams {
   int OHf, OWf, n_valid, group_images;
   int M;               // NB*OH*OW
   int rows_per_group;  // group_images*OH*OW
+  int w_layout;        // 0 = [T][N][C], 1 = [T][C/8][N][8]
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
 };
@@ -38,3 +39,6 @@ int igemm_wgrad_mma(const WgradParams& p, cudaStream_t st);
 // tcgen05 + TMA path (igemm_tc.cu). Returns SV_ERR_UNSUPPORTED when the shape is not covered.
 bool igemm_fprop_tc_supported(const IgemmParams& p);
 int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st);
+// tcgen05 halo-tile path (igemm_halo.cu)
+bool igemm_fprop_halo_supported(const IgemmParams& p);
+int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st);

@@ -401,7 +401,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 }
 
 __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int C, int T, int n_real,
-                                   int c_real, long long sn, long long sc, long long st, TapIdx ti) {
+                                   int c_real, long long sn, long long sc, long long st, TapIdx ti, int layout) {
   const long long total = (long long)T * N * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -410,7 +410,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
     const int t = (int)(r / N);
     float v = 0.f;
     if (n < n_real && c < c_real) v = src[n * sn + c * sc + ti.v[t] * st];
-    dst[i] = __float2bfloat16(v);
+    const long long o = layout == 0 ? i : ((((long long)t * (C >> 3) + (c >> 3)) * N + n) << 3) + (c & 7);
+    dst[o] = __float2bfloat16(v);
   }
 }
 
@@ -448,12 +449,14 @@ extern "C" int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits
 }
 
 extern "C" int sv_pack_weight(const float* src, void* dst, int32_t N, int32_t C, int32_t T, int32_t n_real,
-                              int32_t c_real, int64_t sn, int64_t sc, int64_t st, const int8_t* tap_index, void* stream) {
+                              int32_t c_real, int64_t sn, int64_t sc, int64_t st, const int8_t* tap_index, int32_t layout,
+                              void* stream) {
   SV_REQUIRE(T >= 1 && T <= SV_MAX_TAPS, "sv_pack_weight: bad T");
+  SV_REQUIRE(layout == 0 || (layout == 1 && C % 8 == 0), "sv_pack_weight: bad layout");
   TapIdx ti;
   memcpy(ti.v, tap_index, T);
   const long long total = (long long)T * N * C;
   const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, N, C, T, n_real, c_real, sn, sc, st, ti);
+  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, N, C, T, n_real, c_real, sn, sc, st, ti, layout);
   return sv_check_launch("pack_weight");
 }

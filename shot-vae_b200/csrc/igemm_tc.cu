@@ -1,4 +1,419 @@
-// tcgen05 + TMA implicit-GEMM path (placeholder until the kernel lands: reports "unsupported").
+// Implicit-GEMM convolution on the Blackwell tensor path: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM),
+// operands staged by TMA, persistent warp-specialised CTAs.
+//
+//   out[m, n] = sum_t sum_c A[pixel(m) + (dy_t, dx_t), c] * W[t][n][c]     (stride-1 gathers)
+//
+// * A tile  : 128 output pixels = a box (W_t x H_t x N_t images) of the NHWC activation tensor.  For
+//             each filter tap the producer issues ONE 4-D TMA load of that box shifted by (dy, dx);
+//             out-of-image elements are zero-filled by the TMA unit, which IS the convolution padding.
+// * B tile  : [BN output channels][KB input channels] slice of the packed weights [T][N][C] (3-D TMA).
+// * both tiles land in shared memory in the K-major 64B/128B-swizzled layout tcgen05.mma consumes;
+//   one elected thread issues 128 x BN x 16 MMAs per 16 input channels; accumulators live in TMEM,
+//   double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// * epilogue (4 warps): tcgen05.ld -> +bias, +residual -> bf16 NHWC store (any output stride: serves
+//   transposed-conv / strided-dgrad phases) and per-channel sum / sum^2 for the next BatchNorm.
+//
+// warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+#include <cuda.h>
+#include "common.cuh"
 #include "igemm.h"
-bool igemm_fprop_tc_supported(const IgemmParams&) { return false; }
-int igemm_fprop_tc(const IgemmParams&, cudaStream_t) { sv_set_error("tcgen05 path not built"); return SV_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int BM = 128;
+constexpr int MAX_GROUPS = 4;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+struct TcParams {
+  bf16* out;
+  const bf16* res;
+  const float* bias;
+  float* stats;
+  int M, N, T, KC;           // rows, channels out, taps, k-blocks per tap
+  int OH, OW, OHf, OWf, out_stride, out_off_y, out_off_x;
+  int Wt, Ht, Nt;            // tile box
+  int tiles_h;               // OH / Ht
+  int m_tiles, n_tiles, BN, KB;
+  int rows_per_group, groups;
+  int stages;
+  int swizzle_bytes;         // 64 or 128
+  int8_t dy[SV_MAX_TAPS];
+  int8_t dx[SV_MAX_TAPS];
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) {
+      printf("igemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled operand tile: rows `row_bytes` apart, 8-row groups `8*row_bytes` apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;        // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= layout << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_stat[MAX_GROUPS][2][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = BM * p.KB * 2, b_bytes = p.BN * p.KB * 2;
+  const uint32_t stage_bytes = (a_bytes + b_bytes + 1023) & ~1023u;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int KT = p.T * p.KC;
+  const uint32_t tmem_cols = p.BN <= 32 ? 64 : (p.BN <= 64 ? 128 : 256);   // two accumulator stages
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < MAX_GROUPS * 2 * 128; i += TC_THREADS) (&s_stat[0][0][0])[i] = 0.f;
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================== TMA producer =====================================
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int img0 = (mt / p.tiles_h) * p.Nt;
+      const int h0 = (mt % p.tiles_h) * p.Ht;
+      for (int kb = 0; kb < KT; ++kb) {
+        const int t = kb / p.KC, cb = kb - t * p.KC;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+        tma_load_4d(sa, &tmA, &full_bar[stage], cb * p.KB, (int)p.dx[t], h0 + (int)p.dy[t], img0);
+        tma_load_3d(sa + a_bytes, &tmB, &full_bar[stage], cb * p.KB, nt * p.BN, t);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================== MMA issuer =======================================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t row_bytes = p.KB * 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kb = 0; kb < KT; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint64_t adesc = make_desc(sa, row_bytes), bdesc = make_desc(sa + a_bytes, row_bytes);
+        for (int k = 0; k < p.KB / 16; ++k)
+          tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        tc_commit(&empty_bar[stage]);        // smem slot is free once these MMAs have read it
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue ==========================================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int ohw = p.OH * p.OW;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m = mt * BM + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const int mm = row_ok ? m : 0;
+      const int nb = mm / ohw, r = mm - nb * ohw;
+      const int oh = r / p.OW, ow = r - oh * p.OW;
+      const size_t pix = ((size_t)nb * p.OHf + oh * p.out_stride + p.out_off_y) * p.OWf + ow * p.out_stride + p.out_off_x;
+      const int g = (mt * BM) / p.rows_per_group;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t raw[16];
+        tc_ld16(taddr + c0, raw);
+        tc_ld_wait();
+        float v[16];
+        const int n0 = nt * p.BN + c0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += p.bias[n0 + j];
+        }
+        if (row_ok) {
+          if (p.res != nullptr) {
+            float rr[16];
+            unpack8(*reinterpret_cast<const bf16x8*>(p.res + pix * p.N + n0), rr);
+            unpack8(*reinterpret_cast<const bf16x8*>(p.res + pix * p.N + n0 + 8), rr + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += rr[j];
+          }
+          const bf16x8 o0 = pack8(v), o1 = pack8(v + 8);
+          *reinterpret_cast<bf16x8*>(p.out + pix * p.N + n0) = o0;
+          *reinterpret_cast<bf16x8*>(p.out + pix * p.N + n0 + 8) = o1;
+          unpack8(o0, v);
+          unpack8(o1, v + 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (p.stats != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float s1 = warp_sum(v[j]);
+            const float s2 = warp_sum(v[j] * v[j]);
+            if (lane == j) {
+              atomicAdd(&s_stat[g][0][c0 + j], s1);
+              atomicAdd(&s_stat[g][1][c0 + j], s2);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (p.stats != nullptr && p.n_tiles > 1) {
+        // several n-tiles share the smem accumulators by column index within the tile: flush per tile
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - 128;
+        for (int i = et; i < 2 * p.BN; i += 128) {
+          const int s = i / p.BN, c = i - s * p.BN;
+          const float val = s_stat[g][s][c];
+          if (val != 0.f) atomicAdd(&p.stats[(size_t)(g * 2 + s) * p.N + nt * p.BN + c], val);
+          s_stat[g][s][c] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    if (p.stats != nullptr && p.n_tiles == 1) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = tid - 128;
+      for (int i = et; i < p.groups * 2 * p.BN; i += 128) {
+        const int g = i / (2 * p.BN), rem = i - g * 2 * p.BN;
+        const int s = rem / p.BN, c = rem - s * p.BN;
+        const float val = s_stat[g][s][c];
+        if (val != 0.f) atomicAdd(&p.stats[(size_t)(g * 2 + s) * p.N + c], val);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+struct TileGeom {
+  int Wt, Ht, Nt;
+};
+
+bool tile_geom(int OH, int OW, TileGeom* g) {
+  if (OW <= 0 || OW > BM || (BM % OW) != 0) return false;
+  const int rows = BM / OW;
+  if (OH >= rows) {
+    if (OH % rows) return false;
+    *g = TileGeom{OW, rows, 1};
+    return true;
+  }
+  if (rows % OH) return false;
+  *g = TileGeom{OW, OH, rows / OH};
+  return true;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+bool igemm_fprop_tc_supported(const IgemmParams& p) {
+  TileGeom g;
+  if (p.w_layout != 0) return false;
+  if (p.in_stride != 1 || p.H != p.OH || p.W != p.OW) return false;
+  if (!tile_geom(p.OH, p.OW, &g)) return false;
+  if (p.C % 32 != 0 || p.N % 16 != 0) return false;
+  if (p.N > 128 && p.N % 128 != 0) return false;
+  if (p.out == nullptr || p.outf != nullptr) return false;
+  if (p.stats != nullptr && (p.rows_per_group % BM != 0 || p.NB / p.group_images > MAX_GROUPS)) return false;
+  if (p.NB < g.Nt) return false;
+  if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.Wt) & 15)) return false;
+  return get_encode() != nullptr;
+}
+
+int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { sv_set_error("cuTensorMapEncodeTiled unavailable"); return SV_ERR_UNSUPPORTED; }
+  TileGeom g;
+  if (!tile_geom(p.OH, p.OW, &g)) { sv_set_error("igemm_fprop_tc: unsupported tile geometry"); return SV_ERR_UNSUPPORTED; }
+  TcParams q;
+  memset(&q, 0, sizeof(q));
+  q.out = p.out; q.res = p.res; q.bias = p.bias; q.stats = p.stats;
+  q.M = p.M; q.N = p.N; q.T = p.T;
+  q.KB = (p.C % 64 == 0) ? 64 : 32;
+  q.KC = p.C / q.KB;
+  q.OH = p.OH; q.OW = p.OW; q.OHf = p.OHf; q.OWf = p.OWf;
+  q.out_stride = p.out_stride; q.out_off_y = p.out_off_y; q.out_off_x = p.out_off_x;
+  q.Wt = g.Wt; q.Ht = g.Ht; q.Nt = g.Nt;
+  q.tiles_h = p.OH / g.Ht;
+  q.m_tiles = ceil_div(p.M, BM);
+  // channel tile: whole N when small; otherwise split so that the persistent grid is filled
+  int bn = p.N <= 128 ? p.N : 128;
+  while (bn > 32 && bn % 32 == 0 && q.m_tiles * (p.N / bn) < sm_count() && p.N % (bn / 2) == 0) bn /= 2;
+  q.BN = bn;
+  q.n_tiles = p.N / bn;
+  q.rows_per_group = p.rows_per_group;
+  q.groups = p.NB / p.group_images;
+  q.swizzle_bytes = q.KB * 2;
+  const size_t stage_bytes = ((size_t)BM * q.KB * 2 + (size_t)q.BN * q.KB * 2 + 1023) & ~(size_t)1023;
+  int stages = (int)((192 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { sv_set_error("igemm_fprop_tc: tile too large"); return SV_ERR_UNSUPPORTED; }
+  q.stages = stages;
+  memcpy(q.dy, p.dy, SV_MAX_TAPS);
+  memcpy(q.dx, p.dx, SV_MAX_TAPS);
+
+  const CUtensorMapSwizzle sw = q.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.NB};
+    cuuint64_t strides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)q.KB, (cuuint32_t)g.Wt, (cuuint32_t)g.Ht, (cuuint32_t)g.Nt};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(p.A), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sv_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return SV_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p.C, (cuuint64_t)p.N, (cuuint64_t)p.T};
+    cuuint64_t strides[2] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.N * p.C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)q.KB, (cuuint32_t)q.BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(p.Wt), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sv_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return SV_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(igemm_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = 200 * 1024;
+  }
+  const int total = q.m_tiles * q.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  igemm_fprop_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, q);
+  return sv_check_launch("igemm_fprop_tc");
+}

@@ -27,7 +27,7 @@ class IgemmArgs(C.Structure):
                 ("NB", i32), ("H", i32), ("W", i32), ("C", i32), ("OH", i32), ("OW", i32), ("N", i32), ("T", i32),
                 ("in_stride", i32), ("out_stride", i32), ("out_off_y", i32), ("out_off_x", i32),
                 ("OHf", i32), ("OWf", i32), ("n_valid", i32), ("group_images", i32),
-                ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS), ("impl", i32)]
+                ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS), ("impl", i32), ("w_layout", i32)]
 
 
 class WgradArgs(C.Structure):
@@ -50,9 +50,10 @@ _PROTOS = {
     "sv_sizeof_wgrad_args": (C.c_int, []),
     "sv_sizeof_bn_bwd_term": (C.c_int, []),
     "sv_igemm_fprop": (C.c_int, [C.POINTER(IgemmArgs), vp]),
+    "sv_igemm_fprop_supports": (C.c_int, [C.POINTER(IgemmArgs), i32]),
     "sv_igemm_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "sv_wgrad_reduce": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i8p, vp]),
-    "sv_pack_weight": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i8p, vp]),
+    "sv_pack_weight": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i8p, i32, vp]),
     "sv_pack_image": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "sv_nhwc_to_nchw_f32": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "sv_bn_finalize": (C.c_int, [vp, vp, vp, f32, f32, i32, i32, i32, vp, vp, vp, vp, vp]),
@@ -77,6 +78,7 @@ _PROTOS = {
     "sv_mixup_lerp": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]),
     "sv_pairwise_kl_second_nearest": (C.c_int, [vp, vp, i32, i32, vp, vp, vp]),
     "sv_sgd_step": (C.c_int, [vp, vp, vp, vp, i64, vp]),
+    "sv_debug_halo_trace": (C.c_int, [vp]),
 }
 EXPORTS = sorted(_PROTOS)
 

@@ -12,6 +12,7 @@ Design:
     stride-2 input gradients and transposed convolutions are decomposed into output-parity phases.
 """
 import ctypes as C
+from ctypes import byref
 import math
 import re
 from collections import OrderedDict
@@ -209,11 +210,23 @@ class Net:
         return self.nbt[i:i + 1].view(())
 
     # ---- weight packing recipes ------------------------------------------------------------
-    def _add_pack(self, key, wname, N, C, taps, n_real, c_real, sn, sc, st):
+    def _add_pack(self, key, wname, N, C, taps, n_real, c_real, sn, sc, st, grid=None):
+        """grid = (H, W) of the stride-1 row grid the pack is used on (None: strided gather).  The library
+        is asked whether the halo-tile tcgen05 kernel covers the problem; if so the weights are packed in
+        its 8-channel-plane layout."""
         T = len(taps)
         dst = torch.zeros(T, N, C, dtype=torch.bfloat16, device=self.device)
+        layout = 0
+        if grid is not None and self.impl in (0, 3):
+            a = IgemmArgs()
+            a.A = a.Wt = a.out_bf16 = ptr(dst)
+            a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = 128, grid[0], grid[1], C, grid[0], grid[1], N, T
+            a.in_stride, a.out_stride, a.OHf, a.OWf, a.group_images = 1, 1, grid[0], grid[1], 128
+            a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
+            a.w_layout = 1
+            layout = 1 if lib.sv_igemm_fprop_supports(byref(a), 3) else 0
         self.packs[key] = dict(w=dst, taps=taps, wname=wname, N=N, C=C, T=T, n_real=n_real, c_real=c_real,
-                               sn=sn, sc=sc, st=st, tidx=taps_array([t[0] for t in taps]))
+                               sn=sn, sc=sc, st=st, tidx=taps_array([t[0] for t in taps]), layout=layout)
 
     def _build_packs(self):
         self.packs = OrderedDict()
@@ -222,7 +235,7 @@ class Net:
         cin_p = pad16(self.in_ch)
         # conv0: Conv2d(in_ch, f0, 3, 1, 1, bias) -- OIHW
         self._add_pack("conv0.f", "feature_extractor.encoder.pre_process.conv0.weight", f0, cin_p, conv_taps(3, 1),
-                       f0, self.in_ch, self.in_ch * 9, 9, 1)
+                       f0, self.in_ch, self.in_ch * 9, 9, 1, grid=(32, 32))
         H = 32
         for ui, u in enumerate(topo["units"]):
             Ho = H // u.stride
@@ -234,11 +247,13 @@ class Net:
                 wname = u.prefix + (".i_block.conv.weight" if cname == "sc" else ".f_block.%s.weight" % cname)
                 K = k * k
                 hout = hin // s
-                self._add_pack("u%d.%s.f" % (ui, cname), wname, co, ci, conv_taps(k, pad), co, ci, ci * K, K, 1)
+                self._add_pack("u%d.%s.f" % (ui, cname), wname, co, ci, conv_taps(k, pad), co, ci, ci * K, K, 1,
+                               grid=(hin, hin) if s == 1 else None)
                 for (py, px), taps in dgrad_phase_taps(k, s, pad).items():
                     taps = live_taps(taps, hout, hout, hout, hout, 1)
                     if taps:
-                        self._add_pack("u%d.%s.d%d%d" % (ui, cname, py, px), wname, ci, co, taps, ci, co, K, ci * K, 1)
+                        self._add_pack("u%d.%s.d%d%d" % (ui, cname, py, px), wname, ci, co, taps, ci, co, K, ci * K, 1,
+                                       grid=(hout, hout))
             H = Ho
         # decoder: ConvTranspose2d weights are [Cin, Cout, k, k]
         cin, hin = DEC_CHANNELS[0], 1
@@ -247,7 +262,8 @@ class Net:
             cout_p = pad16(cout)
             for (py, px), taps in dgrad_phase_taps(4, 2, 1).items():
                 taps = live_taps(taps, hin, hin, hin, hin, 1)
-                self._add_pack("d%d.f%d%d" % (li + 1, py, px), wname, cout_p, cin, taps, cout, cin, 16, cout * 16, 1)
+                self._add_pack("d%d.f%d%d" % (li + 1, py, px), wname, cout_p, cin, taps, cout, cin, 16, cout * 16, 1,
+                               grid=(hin, hin) if li < 4 else None)
             taps = live_taps(conv_taps(4, 1), hin, hin, 2 * hin, 2 * hin, 2)
             self._add_pack("d%d.d" % (li + 1), wname, cin, cout_p, taps, cin, cout, cout * 16, 16, 1)
             cin, hin = cout, hin * 2
@@ -257,7 +273,7 @@ class Net:
         st = _abi.stream()
         for pk in self.packs.values():
             check(lib.sv_pack_weight(ptr(self.p(pk["wname"])), ptr(pk["w"]), pk["N"], pk["C"], pk["T"], pk["n_real"],
-                                     pk["c_real"], pk["sn"], pk["sc"], pk["st"], pk["tidx"], st))
+                                     pk["c_real"], pk["sn"], pk["sc"], pk["st"], pk["tidx"], pk["layout"], st))
 
     # ---- low-level launch helpers --------------------------------------------------------------
     def _igemm(self, ctx, key, A, pack, NB, H, W, OH, OW, in_stride=1, out=None, outf=None, res=None, bias=None, stats=None,
@@ -274,11 +290,12 @@ class Net:
             a.OWf = OWf if OWf is not None else OW * out_stride
             a.n_valid, a.group_images = n_valid, ctx.B
             a.dy, a.dx = taps_array([t[1] for t in pk["taps"]]), taps_array([t[2] for t in pk["taps"]])
+            a.w_layout = pk["layout"]
             assert A.shape[-1] == pk["C"], (key, A.shape, pk["C"])
             ctx.args[key] = a
         # operand pointers are refreshed on every call (callers may hand in different tensors)
         a.A, a.out_bf16, a.out_f32, a.residual, a.bias, a.stats = ptr(A), ptr(out), ptr(outf), ptr(res), ptr(bias), ptr(stats)
-        a.impl = self.impl
+        a.impl = 3 if a.w_layout == 1 else (self.impl if self.impl != 3 else 0)
         if self.timing is None:
             check(lib.sv_igemm_fprop(C.byref(a), _abi.stream()))
             return

@@ -42,12 +42,13 @@ def from_nhwc(x):      # NHWC cuda -> NCHW fp32 cpu
     return x.float().cpu().permute(0, 3, 1, 2).contiguous()
 
 
-def pack(sv, w, N, Cc, taps, n_real, c_real, sn, sc, st):
+def pack(sv, w, N, Cc, taps, n_real, c_real, sn, sc, st, impl=1):
+    """packed bf16 weights; the halo-tile kernel (impl 3) takes the 8-channel-plane layout"""
     from shotvae_b200._abi import lib, check, ptr, taps_array
     dst = torch.zeros(len(taps), N, Cc, dtype=torch.bfloat16, device="cuda")
     wd = w.contiguous().cuda()
     check(lib.sv_pack_weight(ptr(wd), ptr(dst), N, Cc, len(taps), n_real, c_real, sn, sc, st, taps_array([t[0] for t in taps]),
-                             sv.stream()))
+                             1 if impl == 3 else 0, sv.stream()))
     return dst
 
 
@@ -62,10 +63,13 @@ def igemm(sv, A, Wt, taps, NB, H, W, Cc, OH, OW, N, in_stride=1, out=None, outf=
     a.n_valid, a.group_images = n_valid, group_images or NB
     a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
     a.impl = impl
+    a.w_layout = 1 if impl == 3 else 0
+    if impl > 1 and not lib.sv_igemm_fprop_supports(C.byref(a), impl):
+        pytest.skip("shape not covered by tcgen05 kernel %d (runs on another kernel)" % impl)
     check(lib.sv_igemm_fprop(C.byref(a), sv.stream()))
 
 
-IMPLS = [1]
+IMPLS = [1, 2, 3]   # 1 = mma.sync, 2 = tcgen05 + per-tap TMA, 3 = tcgen05 halo-tile kernel
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -79,7 +83,7 @@ def test_conv_fprop_matches_torch(sv, impl, cin, cout, H, stride, k, NB):
     bias, resid = torch.randn(cout), bf(torch.randn(NB, cout, H // stride, H // stride))
     want = F.conv2d(x, w, bias, stride, k // 2) + resid
     taps = conv_taps(k, k // 2)
-    Wt = pack(sv, w, cout, cin, taps, cout, cin, cin * k * k, k * k, 1)
+    Wt = pack(sv, w, cout, cin, taps, cout, cin, cin * k * k, k * k, 1, impl)
     Ho = H // stride
     out = torch.empty(NB, Ho, Ho, cout, dtype=torch.bfloat16, device="cuda")
     G = 1 if NB % 2 else 2
@@ -106,7 +110,7 @@ def test_convT_fprop_phases_match_torch(sv, impl, cin, cout, Hin, NB):
     A = nhwc(x)
     for (py, px), taps in dgrad_phase_taps(4, 2, 1).items():
         taps = live_taps(taps, Hin, Hin, Hin, Hin, 1)
-        Wt = pack(sv, w, cp, cin, taps, cout, cin, 16, cout * 16, 1)
+        Wt = pack(sv, w, cp, cin, taps, cout, cin, 16, cout * 16, 1, impl)
         igemm(sv, A, Wt, taps, NB, Hin, Hin, cin, Hin, Hin, cp, out=out, outf=outf, out_stride=2, off=(py, px), OHf=Ho, OWf=Ho,
               n_valid=cout, impl=impl)
     assert rel_rms(from_nhwc(out)[:, :cout], want) < 4e-3
@@ -129,7 +133,7 @@ def test_conv_dgrad_phases_match_autograd(sv, impl, cin, cout, H, stride, k, NB)
         taps = live_taps(taps, Ho, Ho, Ho, Ho, 1)
         if not taps:
             continue
-        Wt = pack(sv, w, cin, cout, taps, cin, cout, k * k, cin * k * k, 1)
+        Wt = pack(sv, w, cin, cout, taps, cin, cout, k * k, cin * k * k, 1, impl)
         igemm(sv, G_, Wt, taps, NB, Ho, Ho, cout, Ho, Ho, cin, out=gin, out_stride=stride, off=(py, px), OHf=H, OWf=H, impl=impl)
     assert rel_rms(from_nhwc(gin), x.grad) < 4e-3
 
