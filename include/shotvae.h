@@ -77,8 +77,13 @@ typedef struct {
   int32_t in_stride, splits;
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
+  int32_t impl;    /* 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 halo-tile kernel */
 } sv_wgrad_args;
 int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream);
+/* The tcgen05 kernel writes one partial slice per persistent CTA: returns the `splits` value the caller
+ * must use (and size `partial` for) if that kernel will run this problem, or 0 if the mma.sync kernel
+ * will (any splits >= 1). */
+int sv_igemm_wgrad_splits(const sv_wgrad_args* a);
 /* grad[n*sn + c*sc + tap_index[t]*st] += sum_s partial[s][n][t*C + c]  for n < n_real, c < c_real */
 int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits, int32_t N, int32_t C, int32_t T,
                     int32_t n_real, int32_t c_real, int64_t sn, int64_t sc, int64_t st,
@@ -88,6 +93,11 @@ int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits, int32_t N
  * layout 0: dst[t][n][c]; layout 1: dst[t][c/8][n][c%8] (8-channel planes, for the halo-tile kernel) */
 int sv_pack_weight(const float* src, void* dst, int32_t N, int32_t C, int32_t T, int32_t n_real, int32_t c_real,
                    int64_t sn, int64_t sc, int64_t st, const int8_t* tap_index /* host */, int32_t layout, void* stream);
+/* All packs of a network in ONE launch.  `table_dev` is a device array of n_packs records
+ * { const float* src; void* dst; int64 sn, sc, st; int32 N, C, T, n_real, c_real, layout; int8 tap[16]; }
+ * (sv_sizeof_pack_desc() bytes each, same meaning as the sv_pack_weight arguments). */
+int sv_pack_weights_batched(const void* table_dev, int32_t n_packs, int32_t blocks_per_pack, void* stream);
+int sv_sizeof_pack_desc(void);
 /* fp32 NCHW [NB, c_real, H, W] -> bf16 NHWC [NB, H, W, C] (zero padded channels) */
 int sv_pack_image(const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream);
 /* fp32 NHWC [NB, HW, c_real] -> fp32 NCHW [NB, c_real, HW] */

@@ -112,17 +112,48 @@ int sv_igemm_fprop(const sv_igemm_args* a, void* stream) {
   return igemm_fprop_mma(p, st);
 }
 
-int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream) {
+static int fill_wgrad(const sv_wgrad_args* a, WgradParams& p) {
   SV_REQUIRE(a && a->A && a->Gr && a->partial, "sv_igemm_wgrad: null operand");
   SV_REQUIRE(a->C % 8 == 0 && a->N % 16 == 0, "sv_igemm_wgrad: C (%d) %% 8, N (%d) %% 16", a->C, a->N);
   SV_REQUIRE(a->T >= 1 && a->T <= SV_MAX_TAPS && a->splits >= 1, "sv_igemm_wgrad: bad T/splits");
-  WgradParams p;
   p.A = (const bf16*)a->A; p.Gr = (const bf16*)a->Gr; p.partial = a->partial;
   p.NB = a->NB; p.H = a->H; p.W = a->W; p.C = a->C; p.OH = a->OH; p.OW = a->OW; p.N = a->N; p.T = a->T;
   p.in_stride = a->in_stride; p.splits = a->splits;
   p.M = a->NB * a->OH * a->OW;
   p.rows_per_split = ((p.M + a->splits - 1) / a->splits + 31) / 32 * 32;
   memcpy(p.dy, a->dy, SV_MAX_TAPS); memcpy(p.dx, a->dx, SV_MAX_TAPS);
+  return SV_OK;
+}
+
+static bool wgrad_uses_tc(const sv_wgrad_args* a, const WgradParams& p) {
+#ifndef SV_NO_TCGEN05
+  if (a->impl == 1) return false;
+  if (a->impl == 0 && !auto_tc_enabled()) return false;
+  return wgrad_halo_supported(p);
+#else
+  return false;
+#endif
+}
+
+int sv_igemm_wgrad_splits(const sv_wgrad_args* a) {
+  WgradParams p;
+  sv_wgrad_args tmp = *a;
+  if (tmp.splits < 1) tmp.splits = 1;
+  if (fill_wgrad(&tmp, p) != SV_OK) return 0;
+#ifndef SV_NO_TCGEN05
+  if (wgrad_uses_tc(a, p)) return wgrad_halo_splits(p);
+#endif
+  return 0;
+}
+
+int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream) {
+  WgradParams p;
+  int rc = fill_wgrad(a, p);
+  if (rc != SV_OK) return rc;
+#ifndef SV_NO_TCGEN05
+  if (wgrad_uses_tc(a, p)) return wgrad_halo(p, (cudaStream_t)stream);
+  SV_REQUIRE(a->impl != 2, "sv_igemm_wgrad: shape not supported by the tcgen05 kernel");
+#endif
   return igemm_wgrad_mma(p, (cudaStream_t)stream);
 }
 

@@ -23,7 +23,7 @@ static ColShape col_shape(long long rows_per_group, int G, int C, int blocks_per
   s.threads = s.cpr * s.rl;
   long long want = (148ll * blocks_per_sm) / (G > 0 ? G : 1);
   if (want < 1) want = 1;
-  long long by_rows = ceil_div_ll(rows_per_group, (long long)s.rl * 4);
+  long long by_rows = ceil_div_ll(rows_per_group, (long long)s.rl * 8);
   s.slabs = (int)(by_rows < want ? by_rows : want);
   if (s.slabs < 1) s.slabs = 1;
   s.slab_rows = ceil_div_ll(rows_per_group, s.slabs);
@@ -65,16 +65,28 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict_
   }
   const long long r0 = (long long)blockIdx.x * slab_rows;
   const long long r1 = min(r0 + slab_rows, rows_per_group);
-  for (long long r = r0 + rl; r < r1; r += nrl) {
-    const size_t off = ((size_t)g * rows_per_group + r) * C + chunk * 8;
-    float v[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(y + off), v);
+  constexpr int U = 4;
+  for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
+    bf16x8 q[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = fmaf(v[j], sc[j], sh[j]);
-      v[j] = t > 0.f ? t : slope * t;
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * nrl;
+      if (r < r1) q[u] = *reinterpret_cast<const bf16x8*>(y + ((size_t)g * rows_per_group + r) * C + chunk * 8);
     }
-    *reinterpret_cast<bf16x8*>(a + off) = pack8(v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * nrl;
+      if (r < r1) {
+        float v[8];
+        unpack8(q[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(v[j], sc[j], sh[j]);
+          v[j] = t > 0.f ? t : slope * t;
+        }
+        *reinterpret_cast<bf16x8*>(a + ((size_t)g * rows_per_group + r) * C + chunk * 8) = pack8(v);
+      }
+    }
   }
 }
 
@@ -230,38 +242,58 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdTerms T, con
   const float inv_hw = 1.f / (float)HW;
   const long long r0 = (long long)blockIdx.x * slab_rows;
   const long long r1 = min(r0 + slab_rows, rows_per_group);
-  for (long long r = r0 + rl; r < r1; r += nrl) {
-    const size_t row = (size_t)g * rows_per_group + r;
-    const size_t off = row * C + chunk * 8;
-    float yv[8], o[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(y + off), yv);
-    if (addend != nullptr) {
-      unpack8(*reinterpret_cast<const bf16x8*>(addend + off), o);
-    } else {
+  constexpr int U = 4;      // rows in flight per thread
+  for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
+    bf16x8 yq[U], aq[U], gq[2][U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.f;
-    }
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * nrl;
+      if (r < r1) {
+        const size_t off = ((size_t)g * rows_per_group + r) * C + chunk * 8;
+        yq[u] = *reinterpret_cast<const bf16x8*>(y + off);
+        if (addend != nullptr) aq[u] = *reinterpret_cast<const bf16x8*>(addend + off);
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (t < T.n) {
-        float gv[8];
-        if (T.t[t].g_feat != nullptr) {
-          const size_t nb = row / HW;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gv[j] = T.t[t].g_feat[nb * C + chunk * 8 + j] * inv_hw;
-        } else {
-          unpack8(*reinterpret_cast<const bf16x8*>((const bf16*)T.t[t].g_a + off), gv);
-        }
-        const float slope = T.t[t].slope;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float pre = fmaf(yv[j], sc[t][j], sh[t][j]);
-          const float gp = pre > 0.f ? gv[j] : slope * gv[j];
-          o[j] += sc[t][j] * gp + k1[t][j] * yv[j] + k0[t][j];
-        }
+        for (int t = 0; t < 2; ++t)
+          if (t < T.n && T.t[t].g_feat == nullptr) gq[t][u] = *reinterpret_cast<const bf16x8*>((const bf16*)T.t[t].g_a + off);
       }
     }
-    *reinterpret_cast<bf16x8*>(g_y + off) = pack8(o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * nrl;
+      if (r < r1) {
+        const size_t row = (size_t)g * rows_per_group + r;
+        const size_t off = row * C + chunk * 8;
+        float yv[8], o[8];
+        unpack8(yq[u], yv);
+        if (addend != nullptr) {
+          unpack8(aq[u], o);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < T.n) {
+            float gv[8];
+            if (T.t[t].g_feat != nullptr) {
+              const size_t nb = row / HW;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gv[j] = T.t[t].g_feat[nb * C + chunk * 8 + j] * inv_hw;
+            } else {
+              unpack8(gq[t][u], gv);
+            }
+            const float slope = T.t[t].slope;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float pre = fmaf(yv[j], sc[t][j], sh[t][j]);
+              const float gp = pre > 0.f ? gv[j] : slope * gv[j];
+              o[j] += sc[t][j] * gp + k1[t][j] * yv[j] + k0[t][j];
+            }
+          }
+        }
+        *reinterpret_cast<bf16x8*>(g_y + off) = pack8(o);
+      }
+    }
   }
 }
 
@@ -352,7 +384,7 @@ int sv_bn_finalize(const float* stats, const float* gamma, const float* beta, fl
 int sv_bn_act_fwd(const void* y, void* a, const float* scale, const float* shift, float slope, int64_t rows_per_group,
                   int32_t G, int32_t C, void* stream) {
   SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_act_fwd: unsupported C=%d", C);
-  const ColShape s = col_shape(rows_per_group, G, C);
+  const ColShape s = col_shape(rows_per_group, G, C, 4);
   bn_act_fwd_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, scale, shift, slope,
                                                                               rows_per_group, s.slab_rows, C);
   return sv_check_launch("bn_act_fwd");
@@ -392,7 +424,7 @@ int sv_bn_bwd_apply(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, 
   memset(&T, 0, sizeof(T));
   T.n = nterms;
   for (int i = 0; i < nterms; ++i) T.t[i] = terms[i];
-  const ColShape s = col_shape(rows_per_group, G, C);
+  const ColShape s = col_shape(rows_per_group, G, C, 4);
   bn_bwd_apply_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(T, (const bf16*)y, (const bf16*)addend,
                                                                                 (bf16*)g_y, eps, rows_per_group, s.slab_rows,
                                                                                 HW, G, C);

@@ -42,3 +42,7 @@ int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st);
 // tcgen05 halo-tile path (igemm_halo.cu)
 bool igemm_fprop_halo_supported(const IgemmParams& p);
 int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st);
+// tcgen05 halo-tile weight gradient (wgrad_halo.cu)
+bool wgrad_halo_supported(const WgradParams& p);
+int wgrad_halo_splits(const WgradParams& p);
+int wgrad_halo(const WgradParams& p, cudaStream_t st);

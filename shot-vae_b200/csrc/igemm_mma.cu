@@ -384,19 +384,23 @@ struct TapIdx {
   int8_t v[SV_MAX_TAPS];
 };
 
+// grid.y slices the splits: every thread sums up to 16 partial slices (independent loads in flight) and
+// adds the result to the FP32 gradient with one atomic (which also gives the += accumulate semantics)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int N, int C,
                                     int T, int n_real, int c_real, long long sn, long long sc, long long st, TapIdx ti) {
   const long long total = (long long)n_real * T * c_real;
   const long long TC = (long long)T * C;
+  const int k0 = blockIdx.y * 16, k1 = min(k0 + 16, splits);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c_real);
     const long long r = i / c_real;
     const int t = (int)(r % T);
     const int n = (int)(r / T);
-    float s = 0.f;
     const float* src = partial + (long long)n * TC + (long long)t * C + c;
-    for (int k = 0; k < splits; ++k) s += src[(long long)k * N * TC];
-    grad[n * sn + c * sc + ti.v[t] * st] += s;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) s[k & 3] += src[(long long)k * N * TC];
+    atomicAdd(&grad[n * sn + c * sc + ti.v[t] * st], (s[0] + s[1]) + (s[2] + s[3]));
   }
 }
 
@@ -415,7 +419,39 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
   }
 }
 
+// one launch for every weight tensor of the network: blockIdx.y selects the pack
+struct PackDesc {
+  const float* src;
+  bf16* dst;
+  long long sn, sc, st;
+  int N, C, T, n_real, c_real, layout;
+  int8_t tap[SV_MAX_TAPS];
+};
+
+__global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ table) {
+  const PackDesc d = table[blockIdx.y];
+  const long long total = (long long)d.T * d.N * d.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d.C);
+    const long long r = i / d.C;
+    const int n = (int)(r % d.N);
+    const int t = (int)(r / d.N);
+    float v = 0.f;
+    if (n < d.n_real && c < d.c_real) v = d.src[n * d.sn + c * d.sc + d.tap[t] * d.st];
+    const long long o = d.layout == 0 ? i : ((((long long)t * (d.C >> 3) + (c >> 3)) * d.N + n) << 3) + (c & 7);
+    d.dst[o] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace
+
+extern "C" int sv_sizeof_pack_desc(void) { return (int)sizeof(PackDesc); }
+
+extern "C" int sv_pack_weights_batched(const void* table_dev, int32_t n_packs, int32_t blocks_per_pack, void* stream) {
+  SV_REQUIRE(table_dev && n_packs > 0 && blocks_per_pack > 0, "sv_pack_weights_batched: bad arguments");
+  pack_weights_batched_kernel<<<dim3(blocks_per_pack, n_packs), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)table_dev);
+  return sv_check_launch("pack_weights_batched");
+}
 
 int igemm_fprop_mma(const IgemmParams& p, cudaStream_t st) {
   const bool k32 = (p.C % 32) == 0;
@@ -444,7 +480,8 @@ extern "C" int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits
   memcpy(ti.v, tap_index, T);
   const long long total = (long long)n_real * T * c_real;
   const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-  wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(partial, grad, splits, N, C, T, n_real, c_real, sn, sc, st, ti);
+  wgrad_reduce_kernel<<<dim3(blocks, (splits + 15) / 16), 256, 0, (cudaStream_t)stream>>>(partial, grad, splits, N, C, T, n_real, c_real,
+                                                                                          sn, sc, st, ti);
   return sv_check_launch("wgrad_reduce");
 }
 

