@@ -152,12 +152,15 @@ def main():
     torch.cuda.set_device(local)
     import torch.distributed as dist
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SHOTVAE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from shot_vae_model.vae import VariationalAutoEncoder
     from shotvae_b200.engine import TrainStep, default_hyper
     from shotvae_b200 import _abi
     from shotvae_b200.ddp import GradReducer
 
+    log = lambda m: print("[bench rank %d] %s" % (rank, m), file=sys.stderr, flush=True)
+    log("process group up" if world > 1 else "single GPU")
     torch.manual_seed(1)
     model = VariationalAutoEncoder(cfg["net"], 3, 0, (32, 32), True, 128, cfg["nd"], 0.67, True).cuda().train()
     hyper = default_hyper(cfg["dataset"], cfg["m2"])
@@ -183,6 +186,7 @@ def main():
     try:
         for i in range(3):                      # allocate buffers, then capture the CUDA graph
             ts.step(*pool[i % len(pool)])
+            log("warm step %d done" % i)
     except Exception as e:                      # capture refused (e.g. a collective that cannot be captured)
         if not use_graph:
             raise
@@ -194,6 +198,7 @@ def main():
     W = max(a.warmup, 3)
     for i in range(W):
         ts.step(*pool[i % len(pool)])
+    log("warm-up done")
     sampler = ClockSampler(local) if rank == 0 else None
     windows = []
     # ---- timed region 1: inputs resident in HBM --------------------------------------------------
@@ -207,6 +212,7 @@ def main():
     sync_all()
     windows.append((w0, time.time()))
     t_res = ev0.elapsed_time(ev1) / 1e3
+    log("resident region done")
     # ---- timed region 2: end to end through TrainStep.step(host tensors) -----------------------------
     sync_all()
     w0 = time.time()
@@ -218,6 +224,7 @@ def main():
     sync_all()
     windows.append((w0, time.time()))
     t_e2e = ev0.elapsed_time(ev1) / 1e3
+    log("e2e region done")
     if world > 1:
         tt = torch.tensor([t_res, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -230,6 +237,7 @@ def main():
     if rank == 0:
         net = model._net
         saved = (ts.use_graph, ts.graph)
+        saved_reducer, ts.reducer = ts.reducer, None      # rank-0-only replay: no collective (the other ranks are not in it)
         ts.use_graph = False
         ts.run_resident()
         net.timing = []
@@ -239,6 +247,7 @@ def main():
         recs = net.timing
         net.timing = None
         ts.use_graph, ts.graph = saved
+        ts.reducer = saved_reducer
         agg = {}
         for kind, key, flops, e0, e1 in recs:
             d = agg.setdefault(kind, dict(ms=0.0, flops=0.0, n=0))

@@ -165,7 +165,19 @@ class TrainStep:
             self.eps.normal_()
             self.unif.uniform_()
 
-    def _sequence(self):
+    def _sequence(self, parts=(0, 1, 2)):
+        """parts: 0 = forwards, losses, backward of [P2|P4] and the decoder backward of [P1|P3] (after it the
+        decoder gradient bucket is final); 1 = rest of the backward; 2 = SGD + BatchNorm running statistics.
+        With several ranks the parts are separate CUDA graphs and the bucket all-reduces are issued between
+        them on a side stream (NCCL is kept out of the captured graphs)."""
+        if 0 in parts:
+            self._part0()
+        if 1 in parts:
+            self._part1()
+        if 2 in parts:
+            self._part2()
+
+    def _part0(self):
         net, B, st = self.net, self.B, _abi.stream()
         nd, D, ch = net.nd, net.ldc, net.in_ch
         cp = pad16(ch)
@@ -217,16 +229,19 @@ class TrainStep:
                                            ptr(g_la2[B:]), ptr(g_mu2[B:]), ptr(g_ls2[B:]), 0, st))
             # ---- backward of [P2 | P4]: heads + encoder only
             net.encoder_bwd(Bc, net.heads_bwd(Bc, g_mu2, g_ls2, g_la2))
-        # ---- backward of [P1 | P3]
-        g_lat = net.decoder_bwd(A, g_rec)
-        if self.reducer is not None:
-            self.reducer.bucket_ready("decoder")
-        net.sample_bwd(A, 0, g_lat, g_mu, g_ls, None, accumulate=1)
-        net.sample_bwd(A, 1, g_lat, g_mu, g_ls, g_la, accumulate=1)
+        # ---- backward of [P1 | P3]: decoder first (its gradients are final afterwards)
+        self._g_lat = net.decoder_bwd(A, g_rec)
+        self._g = (g_mu, g_ls, g_la)
+
+    def _part1(self):
+        net, A = self.net, self.ctxA
+        g_mu, g_ls, g_la = self._g
+        net.sample_bwd(A, 0, self._g_lat, g_mu, g_ls, None, accumulate=1)
+        net.sample_bwd(A, 1, self._g_lat, g_mu, g_ls, g_la, accumulate=1)
         net.encoder_bwd(A, net.heads_bwd(A, g_mu, g_ls, g_la))
-        if self.reducer is not None:
-            self.reducer.bucket_ready("encoder")
-            self.reducer.wait_all()
+
+    def _part2(self):
+        net, A, Bc, st = self.net, self.ctxA, self.ctxB, _abi.stream()
         # ---- optimizer + BatchNorm running statistics
         check(lib.sv_sgd_step(ptr(net.params), ptr(net.grads), ptr(net.momentum), ptr(self.sgd_hyper), net.n_params, st))
         if self.m2:
@@ -237,27 +252,53 @@ class TrainStep:
             net.bn_running_update([(A, 0), (Bc, 0), (A, 1), (Bc, 1)])
 
     # ---- public API --------------------------------------------------------------------------------
+    def _run_parts_eager(self):
+        if self.reducer is None:
+            self._sequence()
+            return
+        self._sequence((0,))
+        self.reducer.bucket_ready("decoder")      # overlaps with the rest of the backward
+        self._sequence((1,))
+        self.reducer.bucket_ready("encoder")
+        self.reducer.wait_all()
+        self._sequence((2,))
+
     def run_resident(self):
         """one optimizer step on the inputs currently resident in the static device buffers"""
         if self._steps_done == 1:
             self.sgd_hyper[4:5].zero_()       # momentum buffer is initialised; torch semantics from now on
         if not self.use_graph:
-            self._sequence()
+            self._run_parts_eager()
         elif self.graph is None and self._steps_done >= 2:
             n0 = _abi.launch_count()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._sequence()
+            groups = [(0, 1, 2)] if self.reducer is None else [(0,), (1,), (2,)]
+            graphs = []
+            for parts in groups:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._sequence(parts)
+                graphs.append(g)
             self.launches_per_step = _abi.launch_count() - n0
-            self.graph = g
-            g.replay()
+            self.graph = graphs
+            self._replay()
         elif self.graph is not None:
-            self.graph.replay()
+            self._replay()
         else:
             n0 = _abi.launch_count()
-            self._sequence()              # eager warm-up steps allocate every buffer
+            self._run_parts_eager()           # eager warm-up steps allocate every buffer
             self.launches_per_step = _abi.launch_count() - n0
         self._steps_done += 1
+
+    def _replay(self):
+        if self.reducer is None:
+            self.graph[0].replay()
+            return
+        self.graph[0].replay()
+        self.reducer.bucket_ready("decoder")
+        self.graph[1].replay()
+        self.reducer.bucket_ready("encoder")
+        self.reducer.wait_all()
+        self.graph[2].replay()
 
     def load_inputs(self, image_l, label_l, image_u, label_u, draws="auto"):
         """host -> device copy of one (labelled, unlabelled) batch pair through pinned staging buffers,

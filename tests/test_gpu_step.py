@@ -345,6 +345,10 @@ def test_engine_graph_replay_equals_eager_sequence():
         for k in ("rec_l", "klc_l", "rec_u", "disc_post_u", "cont_post_u"):
             tol = 1e-3 if i == 0 else (5e-2 if k == "cont_post_u" else 1e-2)
             assert abs(a[k] - b[k]) <= tol * abs(a[k]), (i, k, a[k], b[k])
-    worst = max(rel(s1[k].float(), s0[k].float()) for k in s0 if s0[k].dtype == torch.float32)
-    _report("graph_vs_eager_state_rel", worst)
-    assert worst < 5e-2
+    # parameters after 5 optimizer steps: global relative L2 distance per parameter group (per-tensor maxima are
+    # dominated by tiny tensors whose few elements flip with the atomics' summation order)
+    upd = {k: s1[k].float() for k in s0 if s0[k].dtype == torch.float32 and "running" not in k}
+    wupd = {k: s0[k].float() for k in upd}
+    errs = grad_errors(upd, wupd)
+    _report("graph_vs_eager_state_rel", errs)
+    assert errs["all"] < 2e-2 and errs["decoder"] < 2e-2 and errs["heads"] < 5e-2, errs
