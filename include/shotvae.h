@@ -112,6 +112,11 @@ int sv_bn_finalize(const float* stats, const float* gamma, const float* beta, fl
 /* a = act(y*scale + shift), act = x>0 ? x : slope*x ; y, a bf16 [NB*HW, C] */
 int sv_bn_act_fwd(const void* y, void* a, const float* scale, const float* shift, float slope, int64_t rows_per_group,
                   int32_t G, int32_t C, void* stream);
+/* sv_bn_finalize + sv_bn_act_fwd in one launch (scale/shift derived from the raw statistics in the kernel
+ * prologue; mean/var/scale/shift are still written for the backward pass) */
+int sv_bn_finalize_act_fwd(const void* y, void* a, const float* stats, const float* gamma, const float* beta, float count,
+                           float eps, float slope, int64_t rows_per_group, int32_t G, int32_t C, float* mean, float* var,
+                           float* scale, float* shift, void* stream);
 /* feat[nb][c] = mean_hw act(y*scale+shift)   (transition BN + AdaptiveAvgPool2d, vae.py:107,142) */
 int sv_bn_act_gap_fwd(const void* y, float* feat, const float* scale, const float* shift, float slope, int32_t NB,
                       int32_t HW, int32_t C, int32_t group_images, void* stream);
@@ -138,6 +143,10 @@ int sv_bn_bwd_apply(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, 
 int sv_bn_running_update(const float* const* mean_ptrs, const float* const* var_ptrs, int32_t npass, float count,
                          float momentum, int32_t c_real, float* running_mean, float* running_var,
                          int64_t* num_batches_tracked, void* stream);
+/* every BatchNorm of the step in one launch: `table_dev` = n_bn records { const float* mean[4], var[4]; float*
+ * running_mean, running_var; int64* nbt; float count; int32 npass, C } (sv_sizeof_run_desc() bytes each) */
+int sv_bn_running_update_batched(const void* table_dev, int32_t n_bn, int32_t max_c, float momentum, void* stream);
+int sv_sizeof_run_desc(void);
 /* out[c] += sum_rows x[row][c]  (conv0 bias gradient) */
 int sv_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream);
 

@@ -90,6 +90,86 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict_
   }
 }
 
+// BatchNorm finalize fused into the apply: every thread derives scale/shift of its 8 channels from the raw
+// (sum, sum^2) statistics; block (0, g) also publishes mean / var / scale / shift for the backward pass and
+// the running-statistics update.  Saves one launch per BatchNorm.
+__global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(const bf16* __restrict__ y, bf16* __restrict__ a,
+                                                                  const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float count, float eps, float slope,
+                                                                  long long rows_per_group, long long slab_rows, int C, float* mean,
+                                                                  float* var, float* scale, float* shift) {
+  const int cpr = C / 8;
+  const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
+  const int g = blockIdx.y;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = chunk * 8 + j;
+    const double s1 = stats[(size_t)(g * 2 + 0) * C + c], s2 = stats[(size_t)(g * 2 + 1) * C + c];
+    const double dm = s1 / count;
+    double dv = s2 / count - dm * dm;
+    if (dv < 0.0) dv = 0.0;
+    const float m = (float)dm, v = (float)dv;
+    sc[j] = gamma[c] * rsqrtf(v + eps);
+    sh[j] = beta[c] - m * sc[j];
+    if (blockIdx.x == 0 && rl == 0) {
+      const size_t k = (size_t)g * C + c;
+      mean[k] = m; var[k] = v; scale[k] = sc[j]; shift[k] = sh[j];
+    }
+  }
+  const long long r0 = (long long)blockIdx.x * slab_rows;
+  const long long r1 = min(r0 + slab_rows, rows_per_group);
+  constexpr int U = 4;
+  for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
+    bf16x8 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * nrl;
+      if (r < r1) q[u] = *reinterpret_cast<const bf16x8*>(y + ((size_t)g * rows_per_group + r) * C + chunk * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * nrl;
+      if (r < r1) {
+        float v[8];
+        unpack8(q[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(v[j], sc[j], sh[j]);
+          v[j] = t > 0.f ? t : slope * t;
+        }
+        *reinterpret_cast<bf16x8*>(a + ((size_t)g * rows_per_group + r) * C + chunk * 8) = pack8(v);
+      }
+    }
+  }
+}
+
+struct RunDesc {
+  const float* mean[4];
+  const float* var[4];
+  float* running_mean;
+  float* running_var;
+  long long* nbt;
+  float count;
+  int npass, C;
+};
+
+// every BatchNorm's running-statistics update of the step in one launch (blockIdx.y = BatchNorm)
+__global__ void bn_running_update_batched_kernel(const RunDesc* __restrict__ table, float momentum) {
+  const RunDesc d = table[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && d.nbt != nullptr) *d.nbt += d.npass;
+  if (c >= d.C) return;
+  float rm = d.running_mean[c], rv = d.running_var[c];
+  const float unbias = d.count > 1.f ? d.count / (d.count - 1.f) : 1.f;
+  for (int p = 0; p < d.npass; ++p) {
+    rm = (1.f - momentum) * rm + momentum * d.mean[p][c];
+    rv = (1.f - momentum) * rv + momentum * (d.var[p][c] * unbias);
+  }
+  d.running_mean[c] = rm;
+  d.running_var[c] = rv;
+}
+
 __global__ void bn_act_gap_kernel(const bf16* __restrict__ y, float* __restrict__ feat, const float* __restrict__ scale,
                                   const float* __restrict__ shift, float slope, int NB, int HW, int C, int group_images) {
   const int cpr = C / 8;
@@ -388,6 +468,25 @@ int sv_bn_act_fwd(const void* y, void* a, const float* scale, const float* shift
   bn_act_fwd_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, scale, shift, slope,
                                                                               rows_per_group, s.slab_rows, C);
   return sv_check_launch("bn_act_fwd");
+}
+
+int sv_bn_finalize_act_fwd(const void* y, void* a, const float* stats, const float* gamma, const float* beta, float count, float eps,
+                           float slope, int64_t rows_per_group, int32_t G, int32_t C, float* mean, float* var, float* scale,
+                           float* shift, void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_finalize_act_fwd: unsupported C=%d", C);
+  SV_REQUIRE(y && a && stats && gamma && beta && mean && var && scale && shift, "sv_bn_finalize_act_fwd: null pointer");
+  const ColShape s = col_shape(rows_per_group, G, C, 4);
+  bn_finalize_act_fwd_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)y, (bf16*)a, stats, gamma, beta, count, eps, slope, rows_per_group, s.slab_rows, C, mean, var, scale, shift);
+  return sv_check_launch("bn_finalize_act_fwd");
+}
+
+int sv_sizeof_run_desc(void) { return (int)sizeof(RunDesc); }
+
+int sv_bn_running_update_batched(const void* table_dev, int32_t n_bn, int32_t max_c, float momentum, void* stream) {
+  SV_REQUIRE(table_dev && n_bn > 0 && max_c > 0, "sv_bn_running_update_batched: bad arguments");
+  bn_running_update_batched_kernel<<<dim3(ceil_div(max_c, 128), n_bn), 128, 0, (cudaStream_t)stream>>>((const RunDesc*)table_dev, momentum);
+  return sv_check_launch("bn_running_update_batched");
 }
 
 int sv_bn_act_gap_fwd(const void* y, float* feat, const float* scale, const float* shift, float slope, int32_t NB, int32_t HW,

@@ -42,6 +42,11 @@ class PackDesc(C.Structure):
                 ("tap", C.c_int8 * MAX_TAPS)]
 
 
+class RunDesc(C.Structure):
+    _fields_ = [("mean", vp * 4), ("var", vp * 4), ("running_mean", vp), ("running_var", vp), ("nbt", vp),
+                ("count", f32), ("npass", i32), ("C", i32)]
+
+
 class BnBwdTerm(C.Structure):
     _fields_ = [("g_a", vp), ("g_feat", vp), ("scale", vp), ("shift", vp), ("mean", vp), ("var", vp),
                 ("dgamma", vp), ("dbeta", vp), ("grad_gamma", vp), ("grad_beta", vp), ("slope", f32), ("c_real", i32)]
@@ -67,6 +72,9 @@ _PROTOS = {
     "sv_nhwc_to_nchw_f32": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "sv_bn_finalize": (C.c_int, [vp, vp, vp, f32, f32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "sv_bn_act_fwd": (C.c_int, [vp, vp, vp, vp, f32, i64, i32, i32, vp]),
+    "sv_bn_finalize_act_fwd": (C.c_int, [vp, vp, vp, vp, vp, f32, f32, f32, i64, i32, i32, vp, vp, vp, vp, vp]),
+    "sv_bn_running_update_batched": (C.c_int, [vp, i32, i32, f32, vp]),
+    "sv_sizeof_run_desc": (C.c_int, []),
     "sv_bn_act_gap_fwd": (C.c_int, [vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]),
     "sv_bn_bwd_reduce": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, f32, f32, i64, i32, i32, i32, vp, vp, vp]),
     "sv_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwdTerm), i32, vp, vp, vp, f32, i64, i32, i32, i32, vp]),
@@ -97,7 +105,7 @@ for _name, (_res, _args) in _PROTOS.items():
 
 if lib.sv_abi_version() != 1:
     raise ImportError("libshotvae ABI version %d, binding expects 1" % lib.sv_abi_version())
-for _fn, _st in (("sv_sizeof_pack_desc", PackDesc), ("sv_sizeof_igemm_args", IgemmArgs), ("sv_sizeof_wgrad_args", WgradArgs), ("sv_sizeof_bn_bwd_term", BnBwdTerm)):
+for _fn, _st in (("sv_sizeof_run_desc", RunDesc), ("sv_sizeof_pack_desc", PackDesc), ("sv_sizeof_igemm_args", IgemmArgs), ("sv_sizeof_wgrad_args", WgradArgs), ("sv_sizeof_bn_bwd_term", BnBwdTerm)):
     if getattr(lib, _fn)() != C.sizeof(_st):
         raise ImportError("ctypes mirror of %s is %d bytes, library says %d" % (_st.__name__, C.sizeof(_st), getattr(lib, _fn)()))
 

@@ -71,8 +71,16 @@ class TrainStep:
         # mixup targets
         self.s_mu, self.s_sig, self.s_alpha = z(B, D), z(B, D), z(B, nd)
         self.m_mu, self.m_sig, self.m_alpha = z(B, D), z(B, D), z(B, nd)
-        self.ctxA = Ctx(net, 2, B)
-        self.ctxB = None if m2 else Ctx(net, 2, B)
+        # SHOT step: the two forward launch sequences [P1|P3] and [P2|P4] write into the two halves of ONE
+        # 4-group context, whose encoder/heads backward then runs as a single G=4 launch sequence
+        if m2:
+            self.ctxS = self.ctxA = Ctx(net, 2, B)
+            self.ctxB = None
+        else:
+            self.ctxS = Ctx(net, 4, B)
+            self.ctxA = Ctx(net, 2, B, parent=self.ctxS, g0=0)
+            self.ctxB = Ctx(net, 2, B, parent=self.ctxS, g0=2)
+        self._adopted = False
         self.graph = None
         self.launches_per_step = None
         self._epoch = None
@@ -182,7 +190,7 @@ class TrainStep:
         nd, D, ch = net.nd, net.ldc, net.in_ch
         cp = pad16(ch)
         A, Bc = self.ctxA, self.ctxB
-        A.reset()
+        self.ctxS.reset()
         self.terms.zero_()
         net.pack_weights()
         self._noise()
@@ -201,7 +209,6 @@ class TrainStep:
             check(lib.sv_posterior_fwd_bwd(ptr(la[:B]), None, ptr(self.label_l), None, None, None, None, None, None,
                                            ptr(self.coef[6:]), B, D, nd, ptr(self.terms[6:]), ptr(g_la[:B]), None, None, 1, st))
         else:
-            Bc.reset()
             # ---- label smoothing (P1 -> P2 inputs) and optimal-interpolation mixup (P3 -> P4 inputs)
             xB = Bc.t("x_img", (2 * B, 32, 32, cp))
             check(lib.sv_mixup_lerp(ptr(self.img_l), ptr(mu[:B]), ptr(ls[:B]), ptr(la[:B]), ptr(self.idx_l), ptr(self.lam), B, ch,
@@ -227,18 +234,23 @@ class TrainStep:
             check(lib.sv_posterior_fwd_bwd(ptr(la2[B:]), ptr(self.m_alpha), None, None, None, ptr(mu2[B:]), ptr(ls2[B:]),
                                            ptr(self.m_mu), ptr(self.m_sig), ptr(self.coef[8:]), B, D, nd, ptr(self.terms[8:]),
                                            ptr(g_la2[B:]), ptr(g_mu2[B:]), ptr(g_ls2[B:]), 0, st))
-            # ---- backward of [P2 | P4]: heads + encoder only
-            net.encoder_bwd(Bc, net.heads_bwd(Bc, g_mu2, g_ls2, g_la2))
+            # (the backward of [P2 | P4] -- heads + encoder only -- runs together with [P1 | P3] in part 1)
         # ---- backward of [P1 | P3]: decoder first (its gradients are final afterwards)
         self._g_lat = net.decoder_bwd(A, g_rec)
         self._g = (g_mu, g_ls, g_la)
 
     def _part1(self):
-        net, A = self.net, self.ctxA
+        net, A, S = self.net, self.ctxA, self.ctxS
         g_mu, g_ls, g_la = self._g
         net.sample_bwd(A, 0, self._g_lat, g_mu, g_ls, None, accumulate=1)
         net.sample_bwd(A, 1, self._g_lat, g_mu, g_ls, g_la, accumulate=1)
-        net.encoder_bwd(A, net.heads_bwd(A, g_mu, g_ls, g_la))
+        if S is not A and not self._adopted:
+            net.adopt_views(S)
+            self._adopted = True
+        # heads + encoder backward of ALL pass groups at once (g.mu / g.ls / g.la of the views are slices of S's)
+        D, nd = net.ldc, net.nd
+        net.encoder_bwd(S, net.heads_bwd(S, S.t("g.mu", (S.NB, D), torch.float32), S.t("g.ls", (S.NB, D), torch.float32),
+                                         S.t("g.la", (S.NB, nd), torch.float32)))
 
     def _part2(self):
         net, A, Bc, st = self.net, self.ctxA, self.ctxB, _abi.stream()
@@ -246,10 +258,8 @@ class TrainStep:
         check(lib.sv_sgd_step(ptr(net.params), ptr(net.grads), ptr(net.momentum), ptr(self.sgd_hyper), net.n_params, st))
         if self.m2:
             net.bn_running_update([(A, 0), (A, 1)])
-        elif self.skip_dead_decoders:
-            net.bn_running_update([(A, 0), (Bc, 0), (A, 1), (Bc, 1)])
         else:
-            net.bn_running_update([(A, 0), (Bc, 0), (A, 1), (Bc, 1)])
+            net.bn_running_update([(A, 0), (Bc, 0), (A, 1), (Bc, 1)])     # reference order P1, P2, P3, P4
 
     # ---- public API --------------------------------------------------------------------------------
     def _run_parts_eager(self):

@@ -122,12 +122,17 @@ class Ctx:
     allocated on first use and then reused, so every later pass replays the same addresses
     (CUDA-graph capturable)."""
 
-    def __init__(self, net, G, B):
+    def __init__(self, net, G, B, parent=None, g0=0):
+        """parent/g0: this context is a VIEW of pass groups [g0, g0+G) of `parent` -- every buffer is a slice
+        of the parent's buffer of the same name.  Two G=2 forward passes can then be followed by ONE G=4
+        backward pass over the parent (engine.TrainStep)."""
         self.net, self.G, self.B, self.NB = net, G, B, G * B
         self.dev = net.device
+        self.parent, self.g0 = parent, g0
         self.bufs = {}
         self.args = {}
-        self.zero_arena = torch.zeros(3 * 1024 * 1024, dtype=torch.float32, device=self.dev)
+        if parent is None:
+            self.zero_arena = torch.zeros(3 * 1024 * 1024, dtype=torch.float32, device=self.dev)
         self.zero_used = 0
         self.bn = OrderedDict()   # bn name -> dict(mean, var, count, ...)
         self.tape = []
@@ -135,13 +140,28 @@ class Ctx:
     def t(self, name, shape, dtype=torch.bfloat16):
         b = self.bufs.get(name)
         if b is None:
-            b = torch.empty(shape, dtype=dtype, device=self.dev)
+            if self.parent is not None:
+                if shape[0] == self.NB:        # per-image tensor: slice the images of this view's groups
+                    full = self.parent.t(name, (self.parent.NB,) + tuple(shape[1:]), dtype)
+                    b = full[self.g0 * self.B:(self.g0 + self.G) * self.B]
+                else:                          # per-group tensor ([G][C] BatchNorm coefficients)
+                    assert shape[0] == self.G, (name, shape)
+                    full = self.parent.t(name, (self.parent.G,) + tuple(shape[1:]), dtype)
+                    b = full[self.g0:self.g0 + self.G]
+            else:
+                b = torch.empty(shape, dtype=dtype, device=self.dev)
             self.bufs[name] = b
         return b
 
     def z(self, name, numel):
         """fp32 buffer that is zero at the start of every pass (one memset for all of them)."""
         b = self.bufs.get(name)
+        if b is None and self.parent is not None:
+            per = numel // self.G
+            assert per * self.G == numel, (name, numel)
+            full = self.parent.z(name, per * self.parent.G)
+            b = full[self.g0 * per:(self.g0 + self.G) * per]
+            self.bufs[name] = b
         if b is None:
             n = (numel + 3) // 4 * 4
             assert self.zero_used + n <= self.zero_arena.numel(), "zero arena exhausted"
@@ -151,6 +171,8 @@ class Ctx:
         return b
 
     def reset(self):
+        if self.parent is not None:
+            return              # the parent's arena covers the views
         if self.zero_used:
             self.zero_arena[:self.zero_used].zero_()
         else:
@@ -190,6 +212,7 @@ class Net:
         for k, v in named_buffers.items():
             self.b(k).copy_(v.detach().to(self.device))
         self.wg_ws = torch.empty(WG_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
+        self.dry = False          # dry mode: build buffers / records only, launch nothing (Ctx views -> parent tape)
         self.timing = None        # bench instrumentation: list of (kind, key, flops, ev0, ev1) when enabled
         self._build_packs()
 
@@ -311,6 +334,8 @@ class Net:
         # operand pointers are refreshed on every call (callers may hand in different tensors)
         a.A, a.out_bf16, a.out_f32, a.residual, a.bias, a.stats = ptr(A), ptr(out), ptr(outf), ptr(res), ptr(bias), ptr(stats)
         a.impl = 3 if a.w_layout == 1 else (self.impl if self.impl != 3 else 0)
+        if self.dry:
+            return
         if self.timing is None:
             check(lib.sv_igemm_fprop(C.byref(a), _abi.stream()))
             return
@@ -369,9 +394,27 @@ class Net:
         rec = dict(mean=ctx.t(key + ".mean", (G, Cc), torch.float32), var=ctx.t(key + ".var", (G, Cc), torch.float32),
                    scale=ctx.t(key + ".scale", (G, Cc), torch.float32), shift=ctx.t(key + ".shift", (G, Cc), torch.float32),
                    count=count, C=Cc, name=bn_name)
+        ctx.bn[bn_name] = rec
+        if self.dry:
+            return rec
         check(lib.sv_bn_finalize(ptr(stats), ptr(self.p(bn_name + ".weight")), ptr(self.p(bn_name + ".bias")), float(count),
                                  BN_EPS, G, Cc, Cc, ptr(rec["mean"]), ptr(rec["var"]), ptr(rec["scale"]), ptr(rec["shift"]),
                                  _abi.stream()))
+        ctx.bn[bn_name] = rec
+        return rec
+
+    def _bn_fwd_act(self, ctx, bn_name, key, stats, Cc, count, y, a, slope):
+        """BatchNorm finalize + apply + activation in one launch"""
+        G = ctx.G
+        rec = dict(mean=ctx.t(key + ".mean", (G, Cc), torch.float32), var=ctx.t(key + ".var", (G, Cc), torch.float32),
+                   scale=ctx.t(key + ".scale", (G, Cc), torch.float32), shift=ctx.t(key + ".shift", (G, Cc), torch.float32),
+                   count=count, C=Cc, name=bn_name)
+        ctx.bn[bn_name] = rec
+        if self.dry:
+            return rec
+        check(lib.sv_bn_finalize_act_fwd(ptr(y), ptr(a), ptr(stats), ptr(self.p(bn_name + ".weight")), ptr(self.p(bn_name + ".bias")),
+                                         float(count), BN_EPS, float(slope), count, G, Cc, ptr(rec["mean"]), ptr(rec["var"]),
+                                         ptr(rec["scale"]), ptr(rec["shift"]), _abi.stream()))
         ctx.bn[bn_name] = rec
         return rec
 
@@ -414,21 +457,18 @@ class Net:
             k = "u%d" % ui
             Ho = H // u.stride
             rows_in, rows_out = B * H * H, B * Ho * Ho
-            bn1 = self._bn_fwd(ctx, u.prefix + ".f_block.norm1", k + ".bn1", st, u.cin, rows_in)
             a1 = ctx.t(k + ".a1", (NB, H, H, u.cin))
-            self._bn_act(ctx, h, a1, bn1, slope, rows_in)
+            bn1 = self._bn_fwd_act(ctx, u.prefix + ".f_block.norm1", k + ".bn1", st, u.cin, rows_in, h, a1, slope)
             y1 = ctx.t(k + ".y1", (NB, Ho, Ho, u.cout))
             st1 = ctx.z(k + ".st1", G * 2 * u.cout)
             self._igemm(ctx, k + ".conv1", a1, k + ".conv1.f", NB, H, H, Ho, Ho, in_stride=u.stride, out=y1, stats=st1)
-            bn2 = self._bn_fwd(ctx, u.prefix + ".f_block.norm2", k + ".bn2", st1, u.cout, rows_out)
             a2 = ctx.t(k + ".a2", (NB, Ho, Ho, u.cout))
-            self._bn_act(ctx, y1, a2, bn2, slope, rows_out)
+            bn2 = self._bn_fwd_act(ctx, u.prefix + ".f_block.norm2", k + ".bn2", st1, u.cout, rows_out, y1, a2, slope)
             bns = a_s = None
             res = h
             if u.shortcut:
-                bns = self._bn_fwd(ctx, u.prefix + ".i_block.norm", k + ".bns", st, u.cin, rows_in)
                 a_s = ctx.t(k + ".as", (NB, H, H, u.cin))
-                self._bn_act(ctx, h, a_s, bns, sslope, rows_in)
+                bns = self._bn_fwd_act(ctx, u.prefix + ".i_block.norm", k + ".bns", st, u.cin, rows_in, h, a_s, sslope)
                 res = ctx.t(k + ".s", (NB, Ho, Ho, u.cout))
                 self._igemm(ctx, k + ".sc", a_s, k + ".sc.f", NB, H, H, Ho, Ho, in_stride=u.stride, out=res)
             hn = ctx.t(k + ".h", (NB, Ho, Ho, u.cout))
@@ -439,9 +479,10 @@ class Net:
         Cf = topo["feat"]
         bnT = self._bn_fwd(ctx, "feature_extractor.encoder.transition.norm", "bnT", st, Cf, B * H * H)
         feat = ctx.t("feat", (NB, Cf), torch.float32)
-        check(lib.sv_bn_act_gap_fwd(ptr(h), ptr(feat), ptr(bnT["scale"]), ptr(bnT["shift"]), float(slope), NB, H * H, Cf, B,
-                                    _abi.stream()))
         ctx.enc_out = dict(h=h, H=H, bnT=bnT)
+        if not self.dry:
+            check(lib.sv_bn_act_gap_fwd(ptr(h), ptr(feat), ptr(bnT["scale"]), ptr(bnT["shift"]), float(slope), NB, H * H, Cf, B,
+                                        _abi.stream()))
         return feat
 
     def encoder_bwd(self, ctx, g_feat):
@@ -511,11 +552,13 @@ class Net:
         for hname, short in self.HEADS:
             n = self.nd if short == "logits" else self.ldc
             o = ctx.t(short, (NB, n), torch.float32)
-            check(lib.sv_linear_fwd(ptr(feat), Cf, ptr(self.p(hname + ".fc.weight")), Cf, 0, ptr(self.p(hname + ".fc.bias")),
-                                    ptr(o), None, n, None, 0, NB, n, Cf, s))
+            if not self.dry:
+                check(lib.sv_linear_fwd(ptr(feat), Cf, ptr(self.p(hname + ".fc.weight")), Cf, 0, ptr(self.p(hname + ".fc.bias")),
+                                        ptr(o), None, n, None, 0, NB, n, Cf, s))
             outs[short] = o
         la = ctx.t("la", (NB, self.nd), torch.float32)
-        check(lib.sv_log_softmax_fwd(ptr(outs["logits"]), ptr(la), NB, self.nd, s))
+        if not self.dry:
+            check(lib.sv_log_softmax_fwd(ptr(outs["logits"]), ptr(la), NB, self.nd, s))
         ctx.feat = feat
         return outs["mu"], outs["ls"], la
 
@@ -571,9 +614,8 @@ class Net:
         ctx.dec_latent = latent
         cin, hin = c0, 1
         for li in range(5):
-            bn = self._bn_fwd(ctx, "feature_reconstructor.decoder.%d" % (3 * li + 1), "d%d.bn" % li, st, cin, B * hin * hin)
             a = ctx.t("d%d.a" % li, (NB, hin, hin, cin))
-            self._bn_act(ctx, y, a, bn, 0.0, B * hin * hin)
+            bn = self._bn_fwd_act(ctx, "feature_reconstructor.decoder.%d" % (3 * li + 1), "d%d.bn" % li, st, cin, B * hin * hin, y, a, 0.0)
             ctx.dec.append(dict(y=y, a=a, bn=bn, hin=hin, cin=cin))
             last = li == 4
             cout = self.in_ch if last else DEC_CHANNELS[li + 1]
@@ -620,21 +662,48 @@ class Net:
     # ---- BatchNorm running statistics ----------------------------------------------------------
     def bn_running_update(self, passes):
         """passes: list of (ctx, group) in the order the reference would have executed the forwards
-        (P1, P2, P3, P4 for a SHOT step).  Only BNs that ran in a pass are updated for it."""
-        s = _abi.stream()
-        names = []
-        for ctx, _ in passes:
-            for n in ctx.bn:
-                if n not in names:
-                    names.append(n)
-        for n in names:
-            ps = [(c, gi) for c, gi in passes if n in c.bn]
-            rec0 = ps[0][0].bn[n]
-            Cc = rec0["C"]
-            mp = (C.c_void_p * len(ps))(*[c.bn[n]["mean"][gi].data_ptr() for c, gi in ps])
-            vp_ = (C.c_void_p * len(ps))(*[c.bn[n]["var"][gi].data_ptr() for c, gi in ps])
-            check(lib.sv_bn_running_update(mp, vp_, len(ps), float(rec0["count"]), BN_MOMENTUM, Cc, ptr(self.b(n + ".running_mean")),
-                                           ptr(self.b(n + ".running_var")), ptr(self.b(n + ".num_batches_tracked")), s))
+        (P1, P2, P3, P4 for a SHOT step).  Only BNs that ran in a pass are updated for it.  One launch
+        updates every BatchNorm (descriptor table built once per pass configuration)."""
+        key = tuple((id(c), gi) for c, gi in passes)
+        cache = getattr(self, "_run_tables", None)
+        if cache is None:
+            cache = self._run_tables = {}
+        ent = cache.get(key)
+        if ent is None:
+            names = []
+            for ctx, _ in passes:
+                for n in ctx.bn:
+                    if n not in names:
+                        names.append(n)
+            arr = (_abi.RunDesc * len(names))()
+            max_c = 0
+            for i, n in enumerate(names):
+                ps = [(c, gi) for c, gi in passes if n in c.bn]
+                assert len(ps) <= 4
+                rec0 = ps[0][0].bn[n]
+                d = arr[i]
+                for k, (c, gi) in enumerate(ps):
+                    d.mean[k] = c.bn[n]["mean"][gi].data_ptr()
+                    d.var[k] = c.bn[n]["var"][gi].data_ptr()
+                d.running_mean, d.running_var = ptr(self.b(n + ".running_mean")), ptr(self.b(n + ".running_var"))
+                d.nbt = ptr(self.b(n + ".num_batches_tracked"))
+                d.count, d.npass, d.C = float(rec0["count"]), len(ps), rec0["C"]
+                max_c = max(max_c, rec0["C"])
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+            ent = cache[key] = (table, len(names), max_c)
+        table, n_bn, max_c = ent
+        check(lib.sv_bn_running_update_batched(ptr(table), n_bn, max_c, BN_MOMENTUM, _abi.stream()))
+
+    def adopt_views(self, parent):
+        """After its views ran their forward passes: rebuild the parent's tape / BatchNorm records over the
+        FULL buffers (no launches), so that encoder_bwd / heads_bwd can run once over all pass groups."""
+        self.dry = True
+        try:
+            cp = pad16(self.in_ch)
+            feat = self.encoder_fwd(parent, parent.t("x_img", (parent.NB, 32, 32, cp)))
+            self.heads_fwd(parent, feat)
+        finally:
+            self.dry = False
 
     def zero_grads(self):
         self.grads.zero_()
