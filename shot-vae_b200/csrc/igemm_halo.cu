@@ -58,6 +58,8 @@ struct HaloParams {
   int stages;
   int planes, planes_log2, chunks_per_row;
   int trace, ablate, lag;
+  int staged;               // epilogue goes through shared memory + bulk copies (contiguous output rows)
+  uint32_t stg_off;         // byte offset of the two staging buffers inside dynamic smem
   uint32_t inv_P;           // ceil(65536 / P): s / P == (s * inv_P) >> 16 for the slot range used here
   const bf16* A;
   const bf16* Wp;           // weights packed [T][C/8][N][8]
@@ -100,6 +102,12 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -174,7 +182,7 @@ template <int T_, int KC_>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 igemm_halo_kernel(const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[2], tmem_empty[2], b_bar;
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[2], tmem_empty[2], b_bar, res_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_stat[MAX_GROUPS][2][128];
 
@@ -192,6 +200,7 @@ igemm_halo_kernel(const HaloParams p) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], PRODUCERS); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     mbar_init(&b_bar, 1);
+    mbar_init(&res_bar[0], 1); mbar_init(&res_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < MAX_GROUPS * 2 * 128; i += HL_THREADS) (&s_stat[0][0][0])[i] = 0.f;
@@ -366,9 +375,116 @@ igemm_halo_kernel(const HaloParams p) {
       const uint32_t pix = (uint32_t)((img * p.OHf + oh * p.out_stride + p.out_off_y) * p.OWf + ow * p.out_stride + p.out_off_x);
       const uint32_t obase = pix * (uint32_t)p.N + (uint32_t)(nt * p.BN + cbase);   // element offset (< 2^31 by construction)
       const int g = img / p.group_images;
+      const int img_t = img, jt = j;
       img += img_step; j += j_step;
       if (j >= p.tiles_per_img) { j -= p.tiles_per_img; ++img; }
       if (p.stats != nullptr && g != cur_g) { flush_stats(cur_g); cur_g = g; }
+      if (p.staged) {
+        // ---- staged epilogue: the tile is assembled in shared memory and moved by the bulk-copy engine in
+        // whole image-row segments (W pixels x N channels contiguous in NHWC), so the LSU/L1 path that also
+        // feeds the tensor core's shared-memory operand reads sees no scattered global traffic at all
+        const int b = ti & 1;
+        uint8_t* stg = smem + p.stg_off + (size_t)b * (BM * p.BN * 2);
+        const int s_first = p.P + BM * jt;                 // first slot of the tile
+        const bool elected = (warp == 0 && lane == 0);
+        if (elected) {
+          bulk_wait_read<1>();                             // stores of tile ti-2 have finished reading this buffer
+          if (p.res != nullptr) {
+            // residual: bulk-load the same row segments into the staging buffer
+            uint32_t bytes = 0;
+            for (int y = (int)(((uint32_t)s_first * p.inv_P) >> 16); y <= p.H; ++y) {
+              const int lo = max(s_first, y * p.P + 1), hi = min(s_first + BM, y * p.P + p.W + 1);
+              if (lo >= s_first + BM) break;
+              if (hi > lo) bytes += (uint32_t)(hi - lo) * p.BN * 2;
+            }
+            mbar_expect_tx(&res_bar[b], bytes);
+            for (int y = (int)(((uint32_t)s_first * p.inv_P) >> 16); y <= p.H; ++y) {
+              const int lo = max(s_first, y * p.P + 1), hi = min(s_first + BM, y * p.P + p.W + 1);
+              if (lo >= s_first + BM) break;
+              if (hi > lo) {
+                const size_t gpix = ((size_t)img_t * p.OHf + (y - 1)) * p.OWf + (lo - y * p.P - 1);
+                bulk_load(stg + (size_t)(lo - s_first) * p.BN * 2, p.res + gpix * p.N, (uint32_t)(hi - lo) * p.BN * 2, &res_bar[b]);
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");     // buffer b is free (and residual loads are in flight)
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (p.res != nullptr) mbar_wait(&res_bar[b], (uint32_t)((ti >> 1) & 1));
+        if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][0] = clock64();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + cbase);
+        uint8_t* srow = stg + (size_t)(q * 32 + lane) * p.BN * 2 + (size_t)cbase * 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < nchunk) {
+            const int c0 = k * 16;
+            uint32_t raw[16];
+            tc_ld16(taddr + c0, raw);
+            tc_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(raw[jj]);
+            if (p.bias != nullptr) {
+              const int n0 = nt * p.BN + cbase + c0;
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) v[jj] += p.bias[n0 + jj];
+            }
+            if (row_ok) {
+              if (p.res != nullptr) {
+                float rr[16];
+                unpack8(*reinterpret_cast<const bf16x8*>(srow + c0 * 2), rr);
+                unpack8(*reinterpret_cast<const bf16x8*>(srow + c0 * 2 + 16), rr + 8);
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) v[jj] += rr[jj];
+              }
+              const bf16x8 o0 = pack8(v), o1 = pack8(v + 8);
+              *reinterpret_cast<bf16x8*>(srow + c0 * 2) = o0;
+              *reinterpret_cast<bf16x8*>(srow + c0 * 2 + 16) = o1;
+              if (p.stats != nullptr) { unpack8(o0, v); unpack8(o1, v + 8); }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
+            }
+            if (p.stats != nullptr) {
+              if (reg_stats) {
+                if (k < 2) {
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj) { a1[k][jj] += v[jj]; a2[k][jj] = fmaf(v[jj], v[jj], a2[k][jj]); }
+                }
+              } else {
+                float sq[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) sq[jj] = v[jj] * v[jj];
+                const float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
+                if (lane < 16) {
+                  atomicAdd(&s_stat[g][0][cbase + c0 + lane], s1);
+                  atomicAdd(&s_stat[g][1][cbase + c0 + lane], s2);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);       // accumulator is free as soon as it is in registers
+        fence_proxy_async();                               // st.shared -> visible to the bulk-copy (async) proxy
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (elected) {
+          for (int y = (int)(((uint32_t)s_first * p.inv_P) >> 16); y <= p.H; ++y) {
+            const int lo = max(s_first, y * p.P + 1), hi = min(s_first + BM, y * p.P + p.W + 1);
+            if (lo >= s_first + BM) break;
+            if (hi > lo) {
+              const size_t gpix = ((size_t)img_t * p.OHf + (y - 1)) * p.OWf + (lo - y * p.P - 1);
+              bulk_store(p.out + gpix * p.N, stg + (size_t)(lo - s_first) * p.BN * 2, (uint32_t)(hi - lo) * p.BN * 2);
+            }
+          }
+          bulk_commit();
+        }
+        if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][1] = clock64();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       // residual rows are fetched BEFORE waiting for the accumulator, so their latency is hidden
       bf16x8 rres[8];
       const bool use_res = p.res != nullptr && row_ok;
@@ -437,6 +553,7 @@ igemm_halo_kernel(const HaloParams p) {
       if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][1] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.staged && warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (p.stats != nullptr) {
       flush_stats(cur_g);
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -519,7 +636,17 @@ int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st) {
   q.b_tap_bytes = (uint32_t)(p.C / 8) * q.b_plane_bytes;
   q.b_bytes = (uint32_t)p.T * q.b_tap_bytes;
   const size_t b_alloc = (q.b_bytes + 1023) & ~(size_t)1023;
-  int stages = (int)((196 * 1024 - b_alloc) / q.a_stage_bytes);
+  // staged epilogue: needs contiguous output rows (whole channel range in this CTA, unit output stride)
+  // MEASURED (round 1): correct but ~35 % slower than the direct stores (one elected thread, two 256-thread
+  // barriers and the bulk-copy latency per tile), so it is off unless SHOTVAE_HALO_STAGE=1 (kept for round 2)
+  q.staged = 0;
+  {
+    static int stage_on = -1;
+    if (stage_on < 0) { const char* e = getenv("SHOTVAE_HALO_STAGE"); stage_on = (e && e[0] == '1') ? 1 : 0; }
+    if (stage_on && q.n_tiles == 1 && p.out_stride == 1 && p.OHf == p.H && p.OWf == p.W) q.staged = 1;
+  }
+  const size_t stg_bytes = q.staged ? (size_t)2 * BM * q.BN * 2 : 0;
+  int stages = (int)((196 * 1024 - b_alloc - stg_bytes) / q.a_stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { sv_set_error("igemm_halo: tile does not fit"); return SV_ERR_UNSUPPORTED; }
   q.stages = stages;
@@ -546,7 +673,8 @@ int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st) {
     if (ablate < 0) { const char* e = getenv("SHOTVAE_HALO_ABLATE"); ablate = e ? atoi(e) : 0; }
     q.ablate = ablate;
   }
-  const size_t smem = b_alloc + (size_t)stages * q.a_stage_bytes + 1024;
+  q.stg_off = (uint32_t)(b_alloc + (size_t)stages * q.a_stage_bytes);
+  const size_t smem = b_alloc + (size_t)stages * q.a_stage_bytes + stg_bytes + 1024;
   const int grid = q.ctas_per_nt * q.n_tiles;
   const int kc = p.C / 16;
 #define SV_HALO_CASE(TT, KK)                                                                                   \

@@ -127,7 +127,8 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_stat[MAX_GROUPS][2][128];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = BM * p.KB * 2, b_bytes = p.BN * p.KB * 2;
   const uint32_t stage_bytes = (a_bytes + b_bytes + 1023) & ~1023u;
@@ -171,10 +172,13 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
+    // whole warp runs the loop (warp-uniform descriptor arithmetic on the uniform datapath); one lane issues
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint32_t row_bytes = p.KB * 2;
+    const bool leader = lane == 0;
+    const int ksteps = p.KB / 16;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -186,14 +190,23 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int kb = 0; kb < KT; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sa = smem_u32(smem) + (uint32_t)stage * stage_bytes;
         const uint64_t adesc = make_desc(sa, row_bytes), bdesc = make_desc(sa + a_bytes, row_bytes);
-        for (int k = 0; k < p.KB / 16; ++k)
-          tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-        tc_commit(&empty_bar[stage]);        // smem slot is free once these MMAs have read it
+        if (leader) {
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);        // smem slot is free once these MMAs have read it
+        }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+      if (leader) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
