@@ -352,3 +352,27 @@ def test_engine_graph_replay_equals_eager_sequence():
     errs = grad_errors(upd, wupd)
     _report("graph_vs_eager_state_rel", errs)
     assert errs["all"] < 2e-2 and errs["decoder"] < 2e-2 and errs["heads"] < 5e-2, errs
+
+
+def test_wrn28x10_forward_and_engine_run():
+    """C4 backbone (widths 160/320/640: generic kernels, outside the halo kernel's power-of-two planes)"""
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    net, nd, B = "wideresnet-28-10", 10, 4
+    st = O.init_state(net, nd)
+    il, ll, iu, lu = O.synthetic_batch(B, nd, 7)
+    ost = O.clone_state(st)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        want = O.vae_forward(ost, O.encoder_topology(net), iu, O.LiveDraws(), 0.67)
+    model = build_model(net, nd, st).train()
+    torch.manual_seed(3)
+    with torch.no_grad():
+        got = model(iu.cuda())
+    errs = {n: rel(g, w) for n, g, w in zip(("rec", "mu", "ls", "la"), got, want)}
+    _report("forward_wrn28x10_b4", errs)
+    assert max(errs.values()) < 5e-2, errs
+    ts = TrainStep(model, B, hyper=O.default_hyper("Cifar10"), use_graph=False, device_noise=True)
+    ts.set_epoch(100)
+    t = ts.step(il, ll, iu, lu)
+    assert all(np.isfinite(v) for v in t.values()), t
