@@ -252,11 +252,13 @@ def main():
         ts.use_graph, ts.graph = saved
         ts.reducer = saved_reducer
         agg = {}
-        for kind, key, flops, e0, e1 in recs:
-            d = agg.setdefault(kind, dict(ms=0.0, flops=0.0, n=0))
-            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1
+        for kind, key, flops, e0, e1, nbytes in recs:
+            d = agg.setdefault(kind, dict(ms=0.0, flops=0.0, n=0, bytes=0.0))
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1; d["bytes"] += nbytes
         pk, how = peaks()
-        f = agg.get("igemm_fprop", dict(ms=1e-9, flops=0.0, n=1))
+        f = agg.get("igemm_fprop", dict(ms=1e-9, flops=0.0, n=1, bytes=0.0))
+        hbm_peak = pk.get("hbm_gbs")
+        hbm_ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
         ach = f["flops"] / (f["ms"] * 1e-3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
         step_flops = sum(d["flops"] for d in agg.values()) / 3
@@ -265,18 +267,23 @@ def main():
                     achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None, peak_source=how + ", sustained bf16",
                     launches_per_step=f["n"] // 3, avg_launch_us=1e3 * f["ms"] / max(f["n"], 1),
                     algorithmic_gflop_per_step=step_flops / 1e9,
-                    step_share={k: dict(ms_per_step=d["ms"] / 3, tflops=(d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0),
+                    hbm=dict(achieved=hbm_ach, peak=hbm_peak, unit="GB/s", frac=(hbm_ach / hbm_peak if hbm_peak else None),
+                             algorithmic_mb_per_step=f["bytes"] / 3 / 1e6,
+                             note="same launches against the HBM roof: the 32-channel (32x32) layers sit below the ridge "
+                                  "(~144 FLOP/B vs ~216), the 64/128-channel layers above it"),
+                    step_share={k: dict(ms_per_step=d["ms"] / 3, gbps=d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0, tflops=(d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0),
                                         launches=d["n"] // 3) for k, d in agg.items()},
                     eager_instrumented_ms_per_step=None,
                     measured="CUDA events around every launch of the kernel in an instrumented eager replay of the step "
                              "(3 steps, each queued behind a device-side spin so launches run back to back)")
         if a.dump_kernels:
             per = {}
-            for kind, key, flops, e0, e1 in recs:
-                d = per.setdefault(kind + ":" + key, dict(ms=0.0, flops=flops, n=0))
+            for kind, key, flops, e0, e1, nbytes in recs:
+                d = per.setdefault(kind + ":" + key, dict(ms=0.0, flops=flops, bytes=nbytes, n=0))
                 d["ms"] += e0.elapsed_time(e1); d["n"] += 1
             for d in per.values():
                 d["us"] = 1e3 * d["ms"] / d["n"]; d["tflops"] = d["flops"] / (d["us"] * 1e-6) / 1e12 if d["us"] > 0 else 0
+                d["gbps"] = d["bytes"] / (d["us"] * 1e-6) / 1e9 if d["us"] > 0 else 0
             os.makedirs(os.path.dirname(os.path.abspath(a.dump_kernels)), exist_ok=True)
             json.dump(per, open(a.dump_kernels, "w"), indent=1, sort_keys=True)
 

@@ -72,6 +72,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp.  Unlike `lane == 0`, ptxas knows that exactly one thread passes an
+// elect.sync predicate, so tcgen05.mma / tcgen05.commit behind it are emitted back to back instead of
+// inside a per-active-thread ELECT/BRA.U.ANY serialisation loop (~6 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz));

@@ -41,6 +41,7 @@ constexpr int LAG = 4;          // cp.async groups in flight per producer thread
 constexpr int BM = 128;
 constexpr int MAX_GROUPS = 4;
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_ACC = 8;      // TMEM accumulator ring (the commit -> epilogue signal lags the MMAs by 1-4k cycles under store traffic)
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 constexpr int PAD_SLOTS = 8;   // slack slots (128 B) in front of the A tile: tap (-1,-1) of slot 0 reads 1 slot before it
 
@@ -56,6 +57,8 @@ struct HaloParams {
   int OHf, OWf, out_stride, out_off_y, out_off_x;
   int group_images, groups;
   int stages;
+  int n_acc;                // accumulators in the TMEM ring (n_acc * BN columns, power of two)
+  int one_commit;           // the epilogue releases the A stage (one tcgen05.commit per tile instead of two)
   int planes, planes_log2, chunks_per_row;
   int trace, ablate, lag;
   int staged;               // epilogue goes through shared memory + bulk copies (contiguous output rows)
@@ -182,7 +185,7 @@ template <int T_, int KC_>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 igemm_halo_kernel(const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[2], tmem_empty[2], b_bar, res_bar[2];
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[MAX_ACC], tmem_empty[MAX_ACC], b_bar, res_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_stat[MAX_GROUPS][2][128];
 
@@ -194,11 +197,11 @@ igemm_halo_kernel(const HaloParams p) {
   uint8_t* smem_a = smem + ((p.b_bytes + 1023) & ~1023u);
   const int nt = blockIdx.x % p.n_tiles;
   const int cta = blockIdx.x / p.n_tiles;
-  const uint32_t tmem_cols = p.BN <= 16 ? 32 : (p.BN <= 32 ? 64 : (p.BN <= 64 ? 128 : 256));
+  const uint32_t tmem_cols = (uint32_t)max(32, p.n_acc * p.BN);      // host guarantees a power of two <= 512
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], PRODUCERS); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < p.n_acc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     mbar_init(&b_bar, 1);
     mbar_init(&res_bar[0], 1); mbar_init(&res_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -234,7 +237,6 @@ igemm_halo_kernel(const HaloParams p) {
     const size_t row_elems = (size_t)p.W * p.C;
     int stage = 0, it = 0;
     uint32_t phase = 0;
-    int pub_stage = 0;
     int img = cta / p.tiles_per_img, j = cta - img * p.tiles_per_img;
     const int img_step = p.ctas_per_nt / p.tiles_per_img, j_step = p.ctas_per_nt - img_step * p.tiles_per_img;
     for (int item = cta; item < p.items; item += p.ctas_per_nt, ++it) {
@@ -307,7 +309,8 @@ igemm_halo_kernel(const HaloParams p) {
       if (p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[1][ti][0] = clock64();
       const uint64_t a_desc0 = make_desc_nosw(a_first + (uint32_t)stage * p.a_stage_bytes + (uint32_t)(rel0 * 16), p.a_plane_bytes, 128);
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-      if (leader && !(p.ablate & 4)) {
+      const bool issuer = elect_one();
+      if (issuer && !(p.ablate & 4)) {
 #pragma unroll
         for (int t = 0; t < T_; ++t) {
           // tap (dy, dx) of the A operand == start address shifted by (dy*P + dx) slots of 16 bytes
@@ -319,8 +322,8 @@ igemm_halo_kernel(const HaloParams p) {
                         (t | kc) ? 1u : 0u);
         }
       }
-      if (leader) {
-        tc_commit(&empty_bar[stage]);
+      if (issuer) {
+        if (!p.one_commit) tc_commit(&empty_bar[stage]);
         if (p.trace && blockIdx.x == 0 && ti >= 2 && ti < 5) g_halo_mma_trace[ti - 2][78] = clock64();
         tc_commit(&tmem_full[acc]);
         if (p.trace && blockIdx.x == 0 && ti >= 2 && ti < 5) g_halo_mma_trace[ti - 2][79] = clock64();
@@ -328,7 +331,7 @@ igemm_halo_kernel(const HaloParams p) {
       __syncwarp();
       if (p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[1][ti][1] = clock64();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================================== epilogue (8 warps) ================================
@@ -366,7 +369,7 @@ igemm_halo_kernel(const HaloParams p) {
         for (int jj = 0; jj < 16; ++jj) { a1[k][jj] = 0.f; a2[k][jj] = 0.f; }
       }
     };
-    int ti = 0;
+    int ti = 0, estage = 0;
     for (int item = cta; item < p.items; item += p.ctas_per_nt, ++ti) {
       const int s = p.P + BM * j + q * 32 + lane;      // this thread's output slot
       const int y = (int)(((uint32_t)s * p.inv_P) >> 16), x = s - y * p.P;   // padded coordinates
@@ -411,6 +414,7 @@ igemm_halo_kernel(const HaloParams p) {
         asm volatile("bar.sync 2, 256;" ::: "memory");     // buffer b is free (and residual loads are in flight)
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        if (p.one_commit) { if (warp == 0 && lane == 0) mbar_arrive(&empty_bar[estage]); if (++estage == p.stages) estage = 0; }
         if (p.res != nullptr) mbar_wait(&res_bar[b], (uint32_t)((ti >> 1) & 1));
         if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][0] = clock64();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + cbase);
@@ -482,7 +486,7 @@ igemm_halo_kernel(const HaloParams p) {
           bulk_commit();
         }
         if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][1] = clock64();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       // residual rows are fetched BEFORE waiting for the accumulator, so their latency is hidden
@@ -495,6 +499,8 @@ igemm_halo_kernel(const HaloParams p) {
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      // the tile's MMAs are complete: its A stage can be refilled (saves the MMA warp a second tcgen05.commit)
+      if (p.one_commit) { if (warp == 0 && lane == 0) mbar_arrive(&empty_bar[estage]); if (++estage == p.stages) estage = 0; }
       if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][0] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + cbase);
 #pragma unroll
@@ -551,7 +557,7 @@ igemm_halo_kernel(const HaloParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][1] = clock64();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
     if (p.staged && warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (p.stats != nullptr) {
@@ -651,6 +657,17 @@ int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st) {
   if (stages < 2) { sv_set_error("igemm_halo: tile does not fit"); return SV_ERR_UNSUPPORTED; }
   q.stages = stages;
   q.lag = stages - 1 < LAG ? stages - 1 : LAG;
+  {
+    static int nacc_env = -1, onec_env = -1;
+    if (nacc_env < 0) { const char* e = getenv("SHOTVAE_HALO_NACC"); nacc_env = e ? atoi(e) : 0; }
+    if (onec_env < 0) { const char* e = getenv("SHOTVAE_HALO_ONECOMMIT"); onec_env = e ? atoi(e) : 1; }
+    int n_acc = 512 / q.BN;                   // whole TMEM: nothing else runs on the SM next to a 1-CTA/SM persistent kernel
+    if (n_acc > MAX_ACC) n_acc = MAX_ACC;
+    if (nacc_env > 0 && nacc_env < n_acc) n_acc = nacc_env;
+    while (n_acc & (n_acc - 1)) --n_acc;      // power of two (tcgen05.alloc column counts)
+    q.n_acc = n_acc;
+    q.one_commit = onec_env;
+  }
   int ctas = sm_count() / q.n_tiles;
   if (ctas < 1) ctas = 1;
   if (ctas > q.items) ctas = q.items;

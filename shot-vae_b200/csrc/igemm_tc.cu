@@ -177,7 +177,6 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // whole warp runs the loop (warp-uniform descriptor arithmetic on the uniform datapath); one lane issues
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint32_t row_bytes = p.KB * 2;
-    const bool leader = lane == 0;
     const int ksteps = p.KB / 16;
     int stage = 0;
     uint32_t phase = 0;
@@ -187,12 +186,13 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      const bool issuer = elect_one();      // the same lane issues the tile's MMAs and commits
       for (int kb = 0; kb < KT; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem) + (uint32_t)stage * stage_bytes;
         const uint64_t adesc = make_desc(sa, row_bytes), bdesc = make_desc(sa + a_bytes, row_bytes);
-        if (leader) {
+        if (issuer) {
           if (ksteps == 4) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
@@ -205,7 +205,7 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (leader) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      if (issuer) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

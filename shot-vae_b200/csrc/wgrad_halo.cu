@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
     // idesc: FP32 accumulate, BF16 x BF16, A and B both MN-major, N = C, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.C >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
-    const bool leader = lane == 0;
+    const bool issuer = elect_one();            // one lane issues every MMA and commit of this CTA
     int stage = 0;
     uint32_t phase = 0;
     int j = cta % p.tiles_per_img;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
       const uint32_t sbase = smem_u32(smem) + (uint32_t)stage * p.stage_bytes + PAD_SLOTS * 16;
       const uint64_t g_desc0 = make_desc_mn(sbase + (uint32_t)(rel_g * 16), 128, p.g_plane_bytes);
       const uint64_t a_desc0 = make_desc_mn(sbase + p.a_off + (uint32_t)(rel_a * 16), 128, p.a_plane_bytes);
-      if (leader) {
+      if (issuer) {
 #pragma unroll
         for (int t = 0; t < TG; ++t) {
           if (t < ntaps) {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
       first = 1;
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-    if (leader) tc_commit(&done_bar);
+    if (issuer) tc_commit(&done_bar);
     __syncwarp();
   } else if (warp < 4) {
     // ===================================== final epilogue ====================================

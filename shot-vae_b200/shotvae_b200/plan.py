@@ -213,7 +213,7 @@ class Net:
             self.b(k).copy_(v.detach().to(self.device))
         self.wg_ws = torch.empty(WG_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
         self.dry = False          # dry mode: build buffers / records only, launch nothing (Ctx views -> parent tape)
-        self.timing = None        # bench instrumentation: list of (kind, key, flops, ev0, ev1) when enabled
+        self.timing = None        # bench instrumentation: list of (kind, key, flops, ev0, ev1, algorithmic bytes) when enabled
         self._build_packs()
 
     # ---- views
@@ -345,7 +345,10 @@ class Net:
         e0.record()
         check(lib.sv_igemm_fprop(C.byref(a), _abi.stream()))
         e1.record()
-        self.timing.append(("igemm_fprop", key, flops, e0, e1))
+        esz = lambda t: 0 if t is None else t.numel() * t.element_size()
+        nbytes = esz(A) // (in_stride * in_stride) + esz(pk["w"]) + esz(res) + NB * OH * OW * pk["N"] * ((2 if out is not None else 0) +
+                                                                                                  (4 if outf is not None else 0))
+        self.timing.append(("igemm_fprop", key, flops, e0, e1, nbytes))
 
     def _wgrad(self, ctx, key, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, wname, n_real, c_real, sn, sc, st, exact=False):
         ent = ctx.args.get(key)
@@ -382,8 +385,9 @@ class Net:
             e1.record()
             check(lib.sv_wgrad_reduce(ptr(self.wg_ws), ptr(self.g(wname)), splits, N, Cc, T, n_real, c_real, sn, sc, st, tidx, s))
             e2.record()
-            self.timing.append(("igemm_wgrad", key, flops, e0, e1))
-            self.timing.append(("wgrad_reduce", key, 0.0, e1, e2))
+            nbytes = A.numel() * 2 // (in_stride * in_stride) + Gr.numel() * 2 + splits * N * T * Cc * 4
+            self.timing.append(("igemm_wgrad", key, flops, e0, e1, nbytes))
+            self.timing.append(("wgrad_reduce", key, 0.0, e1, e2, splits * N * T * Cc * 4 + n_real * c_real * T * 8))
             return
         check(lib.sv_igemm_wgrad(C.byref(a), s))
         check(lib.sv_wgrad_reduce(ptr(self.wg_ws), ptr(self.g(wname)), splits, N, Cc, T, n_real, c_real, sn, sc, st, tidx, s))

