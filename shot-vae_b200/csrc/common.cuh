@@ -68,6 +68,24 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return p;
 }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane and instruction.  MEASURED
+// (tools/store_probe.cu): a 128-row tile of 64-byte rows costs ~600 cycles as 2 x 16-byte stores per thread
+// and ~300 as one 32-byte store; 128-byte rows 1330 -> 1010.
+__device__ __forceinline__ void st_global_32B(void* ptr, const bf16x8& a, const bf16x8& b) {
+  const uint32_t* x = reinterpret_cast<const uint32_t*>(&a);
+  const uint32_t* y = reinterpret_cast<const uint32_t*>(&b);
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]),
+               "r"(y[2]), "r"(y[3])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_32B(const void* ptr, bf16x8& a, bf16x8& b) {
+  uint32_t* x = reinterpret_cast<uint32_t*>(&a);
+  uint32_t* y = reinterpret_cast<uint32_t*>(&b);
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3])
+               : "l"(ptr));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -20,9 +20,9 @@
 // reads fully coalesced: one image row = W*C*2 contiguous bytes), published to the tensor core with
 // fence.proxy.async + mbarrier; the resident weights arrive by 1-D bulk copies (cp.async.bulk).
 //
-// warp roles: 0..3 = epilogue (TMEM -> registers -> +bias/+residual -> bf16 NHWC store, BatchNorm
-// sum / sum^2 by a shuffle transpose-reduce), 4 = MMA issuer + TMEM allocator + weight loader,
-// 5..8 = A-tile producers.
+// warp roles (12 warps = 3 per scheduler, so every thread may use 168 registers): 0..3 and 8..11 = epilogue
+// (TMEM -> registers -> +bias/+residual -> bf16 NHWC 32-byte stores, BatchNorm sum / sum^2), 4..6 = A-tile
+// producers, 7 = MMA issuer + TMEM allocator + weight loader.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -35,8 +35,9 @@ __device__ long long g_halo_marks[8];
 
 namespace {
 
-constexpr int HL_THREADS = 416;   // 13 warps: 0-3 + 8-11 epilogue, 4-7 producers, 12 MMA
-constexpr int PRODUCERS = 128;
+constexpr int HL_THREADS = 384;   // 12 warps (3 per scheduler -> 168 registers): 0-3 + 8-11 epilogue, 4-6 producers, 7 MMA
+constexpr int MMA_WARP = 7;
+constexpr int PRODUCERS = 96;
 constexpr int LAG = 4;          // cp.async groups in flight per producer thread before a stage is published
 constexpr int BM = 128;
 constexpr int MAX_GROUPS = 4;
@@ -219,7 +220,7 @@ igemm_halo_kernel(const HaloParams p) {
     }
     fence_proxy_async();
   }
-  if (warp == 12) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -230,7 +231,7 @@ igemm_halo_kernel(const HaloParams p) {
   const uint32_t tmem_base = tmem_base_s;
   if (p.trace && blockIdx.x == 0 && tid == 0) { g_halo_marks[0] = t_entry; g_halo_marks[1] = clock64(); }
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < MMA_WARP) {
     // ===================================== A-tile producers (4 warps) =======================
     const int ptid = tid - 128;
     const bf16* __restrict__ Ag = p.A;
@@ -268,7 +269,7 @@ igemm_halo_kernel(const HaloParams p) {
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
     cp_async_wait<0>();      // do not exit with copies in flight
-  } else if (warp == 12) {
+  } else if (warp == MMA_WARP) {
     // ===================================== MMA issuer =======================================
     // The whole warp runs this loop so that every address / descriptor computation is warp-uniform
     // (uniform datapath, no per-thread register -> uniform register moves in front of each
@@ -494,8 +495,8 @@ igemm_halo_kernel(const HaloParams p) {
       const bool use_res = p.res != nullptr && row_ok;
       if (use_res) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < 2 * nchunk) rres[k] = *reinterpret_cast<const bf16x8*>(p.res + obase + k * 8);
+        for (int k = 0; k < 4; ++k)
+          if (k < nchunk) ld_global_32B(p.res + obase + k * 16, rres[2 * k], rres[2 * k + 1]);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -527,8 +528,7 @@ igemm_halo_kernel(const HaloParams p) {
               for (int jj = 0; jj < 16; ++jj) v[jj] += rr[jj];
             }
             const bf16x8 o0 = pack8(v), o1 = pack8(v + 8);
-            *reinterpret_cast<bf16x8*>(p.out + obase + c0) = o0;
-            *reinterpret_cast<bf16x8*>(p.out + obase + c0 + 8) = o1;
+            st_global_32B(p.out + obase + c0, o0, o1);
             if (p.stats != nullptr) { unpack8(o0, v); unpack8(o1, v + 8); }
           } else {
 #pragma unroll
@@ -576,7 +576,7 @@ igemm_halo_kernel(const HaloParams p) {
   if (p.trace && blockIdx.x == 0 && tid == 0) g_halo_marks[3] = clock64();
   __syncthreads();
   if (p.trace && blockIdx.x == 0 && tid == 0) g_halo_marks[4] = clock64();
-  if (warp == 12) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -613,6 +613,7 @@ bool igemm_fprop_halo_supported(const IgemmParams& p) {
   if (pick_bn(p) == 0) return false;
   if (!(p.T == 1 || p.T == 2 || p.T == 4 || p.T == 9)) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.Wt) & 15)) return false;
+  if ((reinterpret_cast<uintptr_t>(p.out) & 31) || (reinterpret_cast<uintptr_t>(p.res) & 31)) return false;   // 32-byte epilogue accesses
   return true;
 }
 

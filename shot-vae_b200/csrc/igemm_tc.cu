@@ -242,14 +242,15 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (row_ok) {
           if (p.res != nullptr) {
             float rr[16];
-            unpack8(*reinterpret_cast<const bf16x8*>(p.res + pix * p.N + n0), rr);
-            unpack8(*reinterpret_cast<const bf16x8*>(p.res + pix * p.N + n0 + 8), rr + 8);
+            bf16x8 r0, r1;
+            ld_global_32B(p.res + pix * p.N + n0, r0, r1);
+            unpack8(r0, rr);
+            unpack8(r1, rr + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += rr[j];
           }
           const bf16x8 o0 = pack8(v), o1 = pack8(v + 8);
-          *reinterpret_cast<bf16x8*>(p.out + pix * p.N + n0) = o0;
-          *reinterpret_cast<bf16x8*>(p.out + pix * p.N + n0 + 8) = o1;
+          st_global_32B(p.out + pix * p.N + n0, o0, o1);
           unpack8(o0, v);
           unpack8(o1, v + 8);
         } else {
@@ -364,6 +365,7 @@ bool igemm_fprop_tc_supported(const IgemmParams& p) {
   if (p.stats != nullptr && (p.rows_per_group % BM != 0 || p.NB / p.group_images > MAX_GROUPS)) return false;
   if (p.NB < g.Nt) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.Wt) & 15)) return false;
+  if ((reinterpret_cast<uintptr_t>(p.out) & 31) || (reinterpret_cast<uintptr_t>(p.res) & 31)) return false;   // 32-byte epilogue accesses
   return get_encode() != nullptr;
 }
 
