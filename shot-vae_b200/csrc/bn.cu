@@ -281,16 +281,19 @@ struct BwdTerms {
   int n;
 };
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdTerms T, const bf16* __restrict__ y,
+// NT = number of BatchNorm branches fed by y (2 only at a residual unit with a projection shortcut).  The
+// single-branch instantiation keeps half the per-channel coefficients, fits 2 CTAs per SM and streams faster.
+template <int NT>
+__global__ void __launch_bounds__(256, NT == 1 ? 2 : 1) bn_bwd_apply_kernel(const BwdTerms T, const bf16* __restrict__ y,
                                                            const bf16* __restrict__ addend, bf16* __restrict__ g_y, float eps,
                                                            long long rows_per_group, long long slab_rows, int HW, int G, int C) {
   const int cpr = C / 8;
   const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
   const int g = blockIdx.y;
   const float invM = 1.f / (float)rows_per_group;
-  float sc[2][8], sh[2][8], k1[2][8], k0[2][8];
+  float sc[NT][8], sh[NT][8], k1[NT][8], k0[NT][8];
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
+  for (int t = 0; t < NT; ++t) {
     if (t < T.n) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdTerms T, con
   const long long r1 = min(r0 + slab_rows, rows_per_group);
   constexpr int U = 4;      // rows in flight per thread
   for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
-    bf16x8 yq[U], aq[U], gq[2][U];
+    bf16x8 yq[U], aq[U], gq[NT][U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = rb + (long long)u * nrl;
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdTerms T, con
         yq[u] = *reinterpret_cast<const bf16x8*>(y + off);
         if (addend != nullptr) aq[u] = *reinterpret_cast<const bf16x8*>(addend + off);
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < NT; ++t)
           if (t < T.n && T.t[t].g_feat == nullptr) gq[t][u] = *reinterpret_cast<const bf16x8*>((const bf16*)T.t[t].g_a + off);
       }
     }
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdTerms T, con
           for (int j = 0; j < 8; ++j) o[j] = 0.f;
         }
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < NT; ++t) {
           if (t < T.n) {
             float gv[8];
             if (T.t[t].g_feat != nullptr) {
@@ -524,9 +527,12 @@ int sv_bn_bwd_apply(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, 
   T.n = nterms;
   for (int i = 0; i < nterms; ++i) T.t[i] = terms[i];
   const ColShape s = col_shape(rows_per_group, G, C, 4);
-  bn_bwd_apply_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(T, (const bf16*)y, (const bf16*)addend,
-                                                                                (bf16*)g_y, eps, rows_per_group, s.slab_rows,
-                                                                                HW, G, C);
+  if (nterms == 1)
+    bn_bwd_apply_kernel<1><<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(T, (const bf16*)y, (const bf16*)addend, (bf16*)g_y, eps,
+                                                                                     rows_per_group, s.slab_rows, HW, G, C);
+  else
+    bn_bwd_apply_kernel<2><<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(T, (const bf16*)y, (const bf16*)addend, (bf16*)g_y, eps,
+                                                                                     rows_per_group, s.slab_rows, HW, G, C);
   return sv_check_launch("bn_bwd_apply");
 }
 

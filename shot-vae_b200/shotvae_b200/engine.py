@@ -16,6 +16,8 @@ B200-first restructuring of the reference step (results unchanged, see DESIGN.md
 import math
 
 import numpy as np
+import os
+
 import torch
 
 from . import _abi
@@ -54,6 +56,9 @@ class TrainStep:
         self.use_graph, self.device_noise = use_graph, device_noise
         self.skip_dead_decoders = skip_dead_decoders
         self.reducer = reducer
+        # weight gradients overlap the dgrad / BatchNorm-backward chain on a second stream (SHOTVAE_SIDE=0 turns it off)
+        if net.side is None and os.environ.get("SHOTVAE_SIDE", "1") != "0":
+            net.side = torch.cuda.Stream(device=net.device)
         dev, B, nd, D = net.device, self.B, net.nd, net.ldc
         self.dev = dev
         f32, i64 = torch.float32, torch.int64

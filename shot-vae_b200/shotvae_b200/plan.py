@@ -213,6 +213,7 @@ class Net:
             self.b(k).copy_(v.detach().to(self.device))
         self.wg_ws = torch.empty(WG_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
         self.dry = False          # dry mode: build buffers / records only, launch nothing (Ctx views -> parent tape)
+        self.side = None          # optional torch.cuda.Stream for the weight gradients (set by the engine)
         self.timing = None        # bench instrumentation: list of (kind, key, flops, ev0, ev1, algorithmic bytes) when enabled
         self._build_packs()
 
@@ -407,6 +408,17 @@ class Net:
         ctx.bn[bn_name] = rec
         return rec
 
+    def _timed(self, kind, key, nbytes, launch):
+        """bench instrumentation: CUDA events around one launch (only when self.timing is a list)"""
+        if self.timing is None:
+            launch()
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        self.timing.append((kind, key, 0.0, e0, e1, nbytes))
+
     def _bn_fwd_act(self, ctx, bn_name, key, stats, Cc, count, y, a, slope):
         """BatchNorm finalize + apply + activation in one launch"""
         G = ctx.G
@@ -416,9 +428,9 @@ class Net:
         ctx.bn[bn_name] = rec
         if self.dry:
             return rec
-        check(lib.sv_bn_finalize_act_fwd(ptr(y), ptr(a), ptr(stats), ptr(self.p(bn_name + ".weight")), ptr(self.p(bn_name + ".bias")),
-                                         float(count), BN_EPS, float(slope), count, G, Cc, ptr(rec["mean"]), ptr(rec["var"]),
-                                         ptr(rec["scale"]), ptr(rec["shift"]), _abi.stream()))
+        self._timed("bn_fwd_act", key, 4 * y.numel(), lambda: check(lib.sv_bn_finalize_act_fwd(
+            ptr(y), ptr(a), ptr(stats), ptr(self.p(bn_name + ".weight")), ptr(self.p(bn_name + ".bias")), float(count), BN_EPS,
+            float(slope), count, G, Cc, ptr(rec["mean"]), ptr(rec["var"]), ptr(rec["scale"]), ptr(rec["shift"]), _abi.stream())))
         ctx.bn[bn_name] = rec
         return rec
 
@@ -435,15 +447,18 @@ class Net:
         for i, t in enumerate(terms):
             rec = t["rec"]
             dg, db = ctx.z("%s.dg%d" % (key, i), G * Cc), ctx.z("%s.db%d" % (key, i), G * Cc)
-            check(lib.sv_bn_bwd_reduce(ptr(t.get("g_a")), ptr(t.get("g_feat")), ptr(y), ptr(rec["scale"]), ptr(rec["shift"]),
-                                       ptr(rec["mean"]), ptr(rec["var"]), BN_EPS, float(t["slope"]), rows_per_group, HW, G, Cc,
-                                       ptr(dg), ptr(db), s))
+            gb = 2 * t["g_a"].numel() if t.get("g_a") is not None else 0
+            self._timed("bn_bwd_reduce", key, gb + 2 * y.numel(), lambda: check(lib.sv_bn_bwd_reduce(
+                ptr(t.get("g_a")), ptr(t.get("g_feat")), ptr(y), ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"]),
+                BN_EPS, float(t["slope"]), rows_per_group, HW, G, Cc, ptr(dg), ptr(db), s)))
             arr[i].g_a, arr[i].g_feat = ptr(t.get("g_a")), ptr(t.get("g_feat"))
             arr[i].scale, arr[i].shift, arr[i].mean, arr[i].var = ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"])
             arr[i].dgamma, arr[i].dbeta = ptr(dg), ptr(db)
             arr[i].grad_gamma, arr[i].grad_beta = ptr(self.g(rec["name"] + ".weight")), ptr(self.g(rec["name"] + ".bias"))
             arr[i].slope, arr[i].c_real = float(t["slope"]), Cc
-        check(lib.sv_bn_bwd_apply(arr, len(terms), ptr(y), ptr(addend), ptr(g_y), BN_EPS, rows_per_group, HW, G, Cc, s))
+        nb = 2 * y.numel() * (2 + sum(1 for t in terms if t.get("g_a") is not None) + (1 if addend is not None else 0))
+        self._timed("bn_bwd_apply", key, nb, lambda: check(lib.sv_bn_bwd_apply(arr, len(terms), ptr(y), ptr(addend), ptr(g_y), BN_EPS,
+                                                                               rows_per_group, HW, G, Cc, s)))
 
     # ---- encoder -------------------------------------------------------------------------------
     def encoder_fwd(self, ctx, x_img):
@@ -497,29 +512,72 @@ class Net:
         H, Cf = eo["H"], topo["feat"]
         g_h = ctx.t("g.h.%d.%d" % (H, Cf), (NB, H, H, Cf))
         self._bn_bwd(ctx, "bnT", [dict(rec=eo["bnT"], g_feat=g_feat, slope=slope)], eo["h"], None, g_h, B * H * H, H * H)
+        # Weight gradients run on a side stream (when the engine provides one): they only need (activation, output
+        # gradient), so they overlap the dgrad -> BatchNorm-backward chain of the main stream -- tensor-core bound
+        # kernels next to HBM-bound ones.  Buffers shared between units by shape (g.y1.*, the two g.h flip buffers)
+        # are protected by `side_done`: the main stream waits for the previous unit's weight gradients before it
+        # overwrites what they read.
+        side = self.side if not self.dry else None
+        main = torch.cuda.current_stream() if side is not None else None
+        side_done = None
+
+        def ready():
+            """marks the point on the main stream after which a weight gradient's inputs are complete"""
+            if side is None:
+                return None
+            ev = torch.cuda.Event()
+            ev.record(main)
+            return ev
+
+        def on_side(fn, ev):
+            # issued AFTER the main stream's next input-gradient conv (so that conv gets the SMs first and the
+            # weight gradient then shares them with the BatchNorm kernels), but dependent only on `ev`
+            if side is None:
+                fn()
+                return
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                fn()
+
+        def mark_side():
+            if side is None:
+                return None
+            ev = torch.cuda.Event()
+            ev.record(side)
+            return ev
+
         flip = 0
         for rec in reversed(ctx.tape):
             u, k, Hin, Ho = rec["u"], rec["k"], rec["H"], rec["Ho"]
             rows_in, rows_out = B * Hin * Hin, B * Ho * Ho
             g_out = g_h
             K9 = 9
-            # conv2: weight gradient, then input gradient
-            self._wgrad(ctx, k + ".conv2.w", rec["a2"], g_out, conv_taps(3, 1), NB, Ho, Ho, u.cout, Ho, Ho, u.cout, 1,
-                        u.prefix + ".f_block.conv2.weight", u.cout, u.cout, u.cout * K9, K9, 1)
+            # conv2: input gradient (main), weight gradient (side)
+            ev = ready()
             g_a2 = ctx.t("g.a2.%d.%d" % (Ho, u.cout), (NB, Ho, Ho, u.cout))
             self._igemm(ctx, k + ".conv2.d", g_out, k + ".conv2.d00", NB, Ho, Ho, Ho, Ho, out=g_a2)
+            on_side(lambda: self._wgrad(ctx, k + ".conv2.w", rec["a2"], g_out, conv_taps(3, 1), NB, Ho, Ho, u.cout, Ho, Ho, u.cout, 1,
+                                        u.prefix + ".f_block.conv2.weight", u.cout, u.cout, u.cout * K9, K9, 1), ev)
             g_y1 = ctx.t("g.y1.%d.%d" % (Ho, u.cout), (NB, Ho, Ho, u.cout))
+            if side_done is not None:
+                main.wait_event(side_done)      # the previous unit's conv1 weight gradient has read g.y1 / its g_out
             self._bn_bwd(ctx, k + ".bn2", [dict(rec=rec["bn2"], g_a=g_a2, slope=slope)], rec["y1"], None, g_y1, rows_out, Ho * Ho)
-            # conv1
-            self._wgrad(ctx, k + ".conv1.w", rec["a1"], g_y1, conv_taps(3, 1), NB, Hin, Hin, u.cin, Ho, Ho, u.cout, u.stride,
-                        u.prefix + ".f_block.conv1.weight", u.cout, u.cin, u.cin * K9, K9, 1)
+
+            # conv1 (+ projection shortcut)
+            def wgrads1():
+                self._wgrad(ctx, k + ".conv1.w", rec["a1"], g_y1, conv_taps(3, 1), NB, Hin, Hin, u.cin, Ho, Ho, u.cout, u.stride,
+                            u.prefix + ".f_block.conv1.weight", u.cout, u.cin, u.cin * K9, K9, 1)
+                if u.shortcut:
+                    self._wgrad(ctx, k + ".sc.w", rec["a_s"], g_out, conv_taps(1, 0), NB, Hin, Hin, u.cin, Ho, Ho, u.cout, u.stride,
+                                u.prefix + ".i_block.conv.weight", u.cout, u.cin, u.cin, 1, 1)
+            ev = ready()
             g_a1 = ctx.t("g.a1.%d.%d" % (Hin, u.cin), (NB, Hin, Hin, u.cin))
             self._dgrad(ctx, k + ".conv1", g_y1, g_a1, NB, Ho, Hin, u.stride)
+            on_side(wgrads1, ev)
+            side_done = mark_side()
             terms = [dict(rec=rec["bn1"], g_a=g_a1, slope=slope)]
             addend = g_out
             if u.shortcut:
-                self._wgrad(ctx, k + ".sc.w", rec["a_s"], g_out, conv_taps(1, 0), NB, Hin, Hin, u.cin, Ho, Ho, u.cout, u.stride,
-                            u.prefix + ".i_block.conv.weight", u.cout, u.cin, u.cin, 1, 1)
                 g_as = ctx.t("g.as.%d.%d" % (Hin, u.cin), (NB, Hin, Hin, u.cin))
                 self._dgrad(ctx, k + ".sc", g_out, g_as, NB, Ho, Hin, u.stride)
                 terms.append(dict(rec=rec["bns"], g_a=g_as, slope=sslope))
@@ -528,6 +586,8 @@ class Net:
             g_prev = ctx.t("g.h.%d.%d.%d" % (Hin, u.cin, flip), (NB, Hin, Hin, u.cin))
             self._bn_bwd(ctx, k + ".bn1", terms, rec["h_in"], addend, g_prev, rows_in, Hin * Hin)
             g_h = g_prev
+        if side is not None:
+            main.wait_stream(side)
         # conv0: weight + bias gradient (no input gradient: the input is data)
         f0 = topo["f0"]
         cin_p = pad16(self.in_ch)
