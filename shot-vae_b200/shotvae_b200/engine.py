@@ -13,6 +13,7 @@ B200-first restructuring of the reference step (results unchanged, see DESIGN.md
   * with world_size > 1 the gradient arena is all-reduced in buckets on a side stream while the
     remaining backward runs (ddp.py).
 """
+import contextlib
 import math
 
 import numpy as np
@@ -205,15 +206,35 @@ class TrainStep:
         check(lib.sv_pack_image(ptr(self.img_u), ptr(xA[B:]), B, ch, 32 * 32, cp, st))
         feat = net.encoder_fwd(A, xA)
         mu, ls, la = net.heads_fwd(A, feat)
-        net.sample_fwd(A, 0, 0, self.eps[0], label=self.label_l)
-        lat = net.sample_fwd(A, 1, 2, self.eps[2], unif=self.unif[0])
-        rec = net.decoder_fwd(A, lat)
-        g_rec, g_mu, g_ls, g_la = self._losses_first(A, rec)
-        if self.m2:
-            # supervised cross-entropy on the labelled half (main_M2_vae.py:276-277)
-            check(lib.sv_posterior_fwd_bwd(ptr(la[:B]), None, ptr(self.label_l), None, None, None, None, None, None,
-                                           ptr(self.coef[6:]), B, D, nd, ptr(self.terms[6:]), ptr(g_la[:B]), None, None, 1, st))
-        else:
+        # From here two independent chains run until part 1: (a) sample -> decoder forward -> ELBO terms -> decoder
+        # backward of [P1 | P3], and (b) mixup -> encoder forward of [P2 | P4] -> posterior-matching terms.  (a) goes to
+        # the side stream: its many small launches (1x1 ... 8x8 decoder layers, loss reductions) fill the gaps of (b)'s
+        # large persistent convolutions.
+        side = net.side if not self.m2 else None
+        main = torch.cuda.current_stream()
+
+        def fork():
+            if side is None:
+                return contextlib.nullcontext()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            return torch.cuda.stream(side)
+
+        with fork():
+            net.sample_fwd(A, 0, 0, self.eps[0], label=self.label_l)
+            lat = net.sample_fwd(A, 1, 2, self.eps[2], unif=self.unif[0])
+            rec = net.decoder_fwd(A, lat)
+            g_rec, g_mu, g_ls, g_la = self._losses_first(A, rec)
+            if self.m2:
+                # supervised cross-entropy on the labelled half (main_M2_vae.py:276-277)
+                check(lib.sv_posterior_fwd_bwd(ptr(la[:B]), None, ptr(self.label_l), None, None, None, None, None, None,
+                                               ptr(self.coef[6:]), B, D, nd, ptr(self.terms[6:]), ptr(g_la[:B]), None, None, 1,
+                                               _abi.stream()))
+            # backward of [P1 | P3]: decoder first (its gradients are final afterwards)
+            self._g_lat = net.decoder_bwd(A, g_rec)
+            self._g = (g_mu, g_ls, g_la)
+        if not self.m2:
             # ---- label smoothing (P1 -> P2 inputs) and optimal-interpolation mixup (P3 -> P4 inputs)
             xB = Bc.t("x_img", (2 * B, 32, 32, cp))
             check(lib.sv_mixup_lerp(ptr(self.img_l), ptr(mu[:B]), ptr(ls[:B]), ptr(la[:B]), ptr(self.idx_l), ptr(self.lam), B, ch,
@@ -228,9 +249,10 @@ class TrainStep:
             if not self.skip_dead_decoders:
                 # the reconstructions of P2/P4 are discarded by the reference (main_shot_vae.py:311,356) but
                 # their decoder forwards still update the BatchNorm running statistics
-                net.sample_fwd(Bc, 0, 1, self.eps[1], label=self.label_l, label_mix=self.s_lab, lam_dev=self.lam)
-                latB = net.sample_fwd(Bc, 1, 2, self.eps[3], unif=self.unif[1])
-                net.decoder_fwd(Bc, latB)
+                with fork():
+                    net.sample_fwd(Bc, 0, 1, self.eps[1], label=self.label_l, label_mix=self.s_lab, lam_dev=self.lam)
+                    latB = net.sample_fwd(Bc, 1, 2, self.eps[3], unif=self.unif[1])
+                    net.decoder_fwd(Bc, latB)
             g_mu2, g_ls2, g_la2 = Bc.t("g.mu", (2 * B, D), torch.float32), Bc.t("g.ls", (2 * B, D), torch.float32), \
                 Bc.t("g.la", (2 * B, nd), torch.float32)
             check(lib.sv_posterior_fwd_bwd(ptr(la2[:B]), None, ptr(self.label_l), ptr(self.s_lab), ptr(self.lam), ptr(mu2[:B]),
@@ -240,9 +262,8 @@ class TrainStep:
                                            ptr(self.m_mu), ptr(self.m_sig), ptr(self.coef[8:]), B, D, nd, ptr(self.terms[8:]),
                                            ptr(g_la2[B:]), ptr(g_mu2[B:]), ptr(g_ls2[B:]), 0, st))
             # (the backward of [P2 | P4] -- heads + encoder only -- runs together with [P1 | P3] in part 1)
-        # ---- backward of [P1 | P3]: decoder first (its gradients are final afterwards)
-        self._g_lat = net.decoder_bwd(A, g_rec)
-        self._g = (g_mu, g_ls, g_la)
+        if side is not None:
+            main.wait_stream(side)
 
     def _part1(self):
         net, A, S = self.net, self.ctxA, self.ctxS
