@@ -15,6 +15,15 @@ void sv_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool sv_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SHOTVAE_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;     // MEASURED: 6.33 vs 6.35 ms/step inside the CUDA graph -> off by default
+  }
+  return on != 0;
+}
+
 int sv_check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();

@@ -54,6 +54,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict__ y, bf16* __restrict__ a,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          float slope, long long rows_per_group, long long slab_rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int cpr = C / 8;
   const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
   const int g = blockIdx.y;
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(const bf16* __
                                                                   const float* __restrict__ beta, float count, float eps, float slope,
                                                                   long long rows_per_group, long long slab_rows, int C, float* mean,
                                                                   float* var, float* scale, float* shift) {
+  pdl_trigger();
+  pdl_wait();
   const int cpr = C / 8;
   const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
   const int g = blockIdx.y;
@@ -172,6 +176,8 @@ __global__ void bn_running_update_batched_kernel(const RunDesc* __restrict__ tab
 
 __global__ void bn_act_gap_kernel(const bf16* __restrict__ y, float* __restrict__ feat, const float* __restrict__ scale,
                                   const float* __restrict__ shift, float slope, int NB, int HW, int C, int group_images) {
+  pdl_trigger();
+  pdl_wait();
   const int cpr = C / 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)NB * cpr) return;
@@ -206,6 +212,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
                                                             const float* __restrict__ var, float eps, float slope,
                                                             long long rows_per_group, long long slab_rows, int HW, int C,
                                                             float* dgamma, float* dbeta) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_acc[];  // [2][C]
   const int cpr = C / 8;
   const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
@@ -287,6 +295,8 @@ template <int NT>
 __global__ void __launch_bounds__(256, NT == 1 ? 2 : 1) bn_bwd_apply_kernel(const BwdTerms T, const bf16* __restrict__ y,
                                                            const bf16* __restrict__ addend, bf16* __restrict__ g_y, float eps,
                                                            long long rows_per_group, long long slab_rows, int HW, int G, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int cpr = C / 8;
   const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
   const int g = blockIdx.y;
@@ -468,7 +478,7 @@ int sv_bn_act_fwd(const void* y, void* a, const float* scale, const float* shift
                   int32_t G, int32_t C, void* stream) {
   SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_act_fwd: unsupported C=%d", C);
   const ColShape s = col_shape(rows_per_group, G, C, 4);
-  bn_act_fwd_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)a, scale, shift, slope,
+  sv_launch_pdl(bn_act_fwd_kernel, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, (const bf16*)y, (bf16*)a, scale, shift, slope,
                                                                               rows_per_group, s.slab_rows, C);
   return sv_check_launch("bn_act_fwd");
 }
@@ -479,7 +489,7 @@ int sv_bn_finalize_act_fwd(const void* y, void* a, const float* stats, const flo
   SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_finalize_act_fwd: unsupported C=%d", C);
   SV_REQUIRE(y && a && stats && gamma && beta && mean && var && scale && shift, "sv_bn_finalize_act_fwd: null pointer");
   const ColShape s = col_shape(rows_per_group, G, C, 4);
-  bn_finalize_act_fwd_kernel<<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(
+  sv_launch_pdl(bn_finalize_act_fwd_kernel, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, 
       (const bf16*)y, (bf16*)a, stats, gamma, beta, count, eps, slope, rows_per_group, s.slab_rows, C, mean, var, scale, shift);
   return sv_check_launch("bn_finalize_act_fwd");
 }
@@ -496,7 +506,7 @@ int sv_bn_act_gap_fwd(const void* y, float* feat, const float* scale, const floa
                       int32_t C, int32_t group_images, void* stream) {
   SV_REQUIRE(C % 8 == 0, "sv_bn_act_gap_fwd: C %% 8");
   const long long n = (long long)NB * (C / 8);
-  bn_act_gap_kernel<<<(int)ceil_div_ll(n, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)y, feat, scale, shift, slope, NB,
+  sv_launch_pdl(bn_act_gap_kernel, dim3((int)ceil_div_ll(n, 128)), dim3(128), 0, (cudaStream_t)stream, (const bf16*)y, feat, scale, shift, slope, NB,
                                                                                HW, C, group_images);
   return sv_check_launch("bn_act_gap");
 }
@@ -509,10 +519,10 @@ int sv_bn_bwd_reduce(const void* g_a, const float* g_feat, const void* y, const 
   const ColShape s = col_shape(rows_per_group, G, C, 2);   // few blocks: each ends with 2*C global atomics
   const size_t smem = 2 * (size_t)C * sizeof(float);
   if (g_feat)
-    bn_bwd_reduce_kernel<true><<<dim3(s.slabs, G), s.threads, smem, (cudaStream_t)stream>>>(
+    sv_launch_pdl(bn_bwd_reduce_kernel<true>, dim3(s.slabs, G), dim3(s.threads), smem, (cudaStream_t)stream, 
         nullptr, g_feat, (const bf16*)y, scale, shift, mean, var, eps, slope, rows_per_group, s.slab_rows, HW, C, dgamma, dbeta);
   else
-    bn_bwd_reduce_kernel<false><<<dim3(s.slabs, G), s.threads, smem, (cudaStream_t)stream>>>(
+    sv_launch_pdl(bn_bwd_reduce_kernel<false>, dim3(s.slabs, G), dim3(s.threads), smem, (cudaStream_t)stream, 
         (const bf16*)g_a, nullptr, (const bf16*)y, scale, shift, mean, var, eps, slope, rows_per_group, s.slab_rows, HW, C,
         dgamma, dbeta);
   return sv_check_launch("bn_bwd_reduce");
@@ -528,10 +538,10 @@ int sv_bn_bwd_apply(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, 
   for (int i = 0; i < nterms; ++i) T.t[i] = terms[i];
   const ColShape s = col_shape(rows_per_group, G, C, 4);
   if (nterms == 1)
-    bn_bwd_apply_kernel<1><<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(T, (const bf16*)y, (const bf16*)addend, (bf16*)g_y, eps,
+    sv_launch_pdl(bn_bwd_apply_kernel<1>, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, T, (const bf16*)y, (const bf16*)addend, (bf16*)g_y, eps,
                                                                                      rows_per_group, s.slab_rows, HW, G, C);
   else
-    bn_bwd_apply_kernel<2><<<dim3(s.slabs, G), s.threads, 0, (cudaStream_t)stream>>>(T, (const bf16*)y, (const bf16*)addend, (bf16*)g_y, eps,
+    sv_launch_pdl(bn_bwd_apply_kernel<2>, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, T, (const bf16*)y, (const bf16*)addend, (bf16*)g_y, eps,
                                                                                      rows_per_group, s.slab_rows, HW, G, C);
   return sv_check_launch("bn_bwd_apply");
 }

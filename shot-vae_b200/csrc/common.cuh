@@ -22,6 +22,31 @@ int sv_check_launch(const char* what);
     }                                                                                             \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------
+// Kernels launched with sv_launch_pdl may start while their stream predecessor is still draining: everything
+// before pdl_wait() (barrier init, TMEM allocation, shared-memory zeroing) overlaps the predecessor's tail;
+// pdl_wait() returns once the predecessor grid has completed and its memory is visible, so no global access
+// may precede it.  pdl_trigger() lets the successor begin launching.  Opt-in: SHOTVAE_PDL=1 (no measurable gain inside the step graph).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool sv_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t sv_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = sv_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 

@@ -191,6 +191,7 @@ igemm_halo_kernel(const HaloParams p) {
   __shared__ float s_stat[MAX_GROUPS][2][128];
 
   const long long t_entry = clock64();
+  pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -229,6 +230,8 @@ igemm_halo_kernel(const HaloParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  // everything above touched only shared / tensor memory and overlapped the previous kernel's tail
+  pdl_wait();
   if (p.trace && blockIdx.x == 0 && tid == 0) { g_halo_marks[0] = t_entry; g_halo_marks[1] = clock64(); }
 
   if (warp >= 4 && warp < MMA_WARP) {
@@ -702,7 +705,7 @@ int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st) {
       cudaFuncSetAttribute(igemm_halo_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
       configured = true;                                                                                       \
     }                                                                                                          \
-    igemm_halo_kernel<TT, KK><<<grid, HL_THREADS, smem, st>>>(q);                                              \
+    sv_launch_pdl(igemm_halo_kernel<TT, KK>, dim3(grid), dim3(HL_THREADS), smem, st, q);                                              \
     return sv_check_launch("igemm_halo");                                                                      \
   }
 #define SV_HALO_TAPS(TT) SV_HALO_CASE(TT, 1) SV_HALO_CASE(TT, 2) SV_HALO_CASE(TT, 4) SV_HALO_CASE(TT, 8)

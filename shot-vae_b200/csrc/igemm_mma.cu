@@ -31,6 +31,8 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint
 // ------------------------------------------------------------------------------------------------
 template <int BN, int BK>
 __global__ void __launch_bounds__(256) igemm_fprop_mma_kernel(const IgemmParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int BM = 128, STAGES = 3, LDS = BK + 8, CPR = BK / 8;
   constexpr int WARPS_N = (BN >= 64) ? 2 : 1;
   constexpr int WARPS_M = 8 / WARPS_N;
@@ -235,7 +237,7 @@ int launch_fprop(const IgemmParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN));
-  igemm_fprop_mma_kernel<BN, BK><<<grid, 256, smem, st>>>(p);
+  sv_launch_pdl(igemm_fprop_mma_kernel<BN, BK>, dim3(grid), dim3(256), smem, st, p);
   return sv_check_launch("igemm_fprop_mma");
 }
 
@@ -244,6 +246,8 @@ int launch_fprop(const IgemmParams& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 template <int BMN>
 __global__ void __launch_bounds__(256) igemm_wgrad_mma_kernel(const WgradParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int BV = 128, BKP = 32, STAGES = 3;
   constexpr int LDG = BMN + 8, LDA = BV + 8;
   constexpr int WARPS_M = (BMN >= 32) ? 2 : 1;
@@ -376,7 +380,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(p.splits, ceil_div(p.T * p.C, BV), ceil_div(p.N, BMN));
-  igemm_wgrad_mma_kernel<BMN><<<grid, 256, smem, st>>>(p);
+  sv_launch_pdl(igemm_wgrad_mma_kernel<BMN>, dim3(grid), dim3(256), smem, st, p);
   return sv_check_launch("igemm_wgrad_mma");
 }
 
@@ -388,6 +392,8 @@ struct TapIdx {
 // adds the result to the FP32 gradient with one atomic (which also gives the += accumulate semantics)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int N, int C,
                                     int T, int n_real, int c_real, long long sn, long long sc, long long st, TapIdx ti) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n_real * T * c_real;
   const long long TC = (long long)T * C;
   const int k0 = blockIdx.y * 16, k1 = min(k0 + 16, splits);
@@ -431,7 +437,12 @@ struct PackDesc {
 __global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ table) {
   const PackDesc d = table[blockIdx.y];
   const long long total = (long long)d.T * d.N * d.C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  // blocks in proportion to the pack (the 8.4 M-element decoder weight next to 9 K-element 1x1 shortcuts): ~16
+  // elements per thread, the surplus blocks of small packs leave at once
+  const long long want = (total + 256 * 16 - 1) / (256 * 16);
+  const int nblk = (int)(want < (long long)gridDim.x ? want : (long long)gridDim.x);
+  if ((int)blockIdx.x >= nblk) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)nblk * blockDim.x) {
     const int c = (int)(i % d.C);
     const long long r = i / d.C;
     const int n = (int)(r % d.N);
@@ -458,8 +469,14 @@ int igemm_fprop_mma(const IgemmParams& p, cudaStream_t st) {
   const int N = p.N;
 #define SV_DISPATCH(BNV)                                                     \
   return k32 ? launch_fprop<BNV, 32>(p, st) : launch_fprop<BNV, 16>(p, st);
-  if (N % 128 == 0) { SV_DISPATCH(128) }
-  if (N % 64 == 0) { SV_DISPATCH(64) }
+  // widest tile that still gives about one CTA per SM: the decoder's input-gradient GEMMs have M = 256 ... 4096
+  // rows and K up to 4096, and ran 50-100 us on 16-64 CTAs (latency bound) with the widest tile
+  const int m_tiles = ceil_div(p.M, 128);
+  auto enough = [&](int bn) { return m_tiles * (N / bn) >= 120; };
+  if (N % 128 == 0 && enough(128)) { SV_DISPATCH(128) }
+  if (N % 64 == 0 && enough(64)) { SV_DISPATCH(64) }
+  if (N % 32 == 0 && enough(32)) { SV_DISPATCH(32) }
+  if (N % 16 == 0 && (enough(16) || N % 32 != 0)) { SV_DISPATCH(16) }
   if (N % 32 == 0) { SV_DISPATCH(32) }
   SV_DISPATCH(16)
 #undef SV_DISPATCH
@@ -480,7 +497,7 @@ extern "C" int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits
   memcpy(ti.v, tap_index, T);
   const long long total = (long long)n_real * T * c_real;
   const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-  wgrad_reduce_kernel<<<dim3(blocks, (splits + 15) / 16), 256, 0, (cudaStream_t)stream>>>(partial, grad, splits, N, C, T, n_real, c_real,
+  sv_launch_pdl(wgrad_reduce_kernel, dim3(blocks, (splits + 15) / 16), dim3(256), 0, (cudaStream_t)stream, partial, grad, splits, N, C, T, n_real, c_real,
                                                                                           sn, sc, st, ti);
   return sv_check_launch("wgrad_reduce");
 }

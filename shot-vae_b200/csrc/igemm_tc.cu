@@ -127,6 +127,7 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_stat[MAX_GROUPS][2][128];
 
+  pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -151,6 +152,7 @@ igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
@@ -429,6 +431,6 @@ int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st) {
   }
   const int total = q.m_tiles * q.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  igemm_fprop_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, q);
+  sv_launch_pdl(igemm_fprop_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, q);
   return sv_check_launch("igemm_fprop_tc");
 }

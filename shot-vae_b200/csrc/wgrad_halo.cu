@@ -46,6 +46,7 @@ struct WgParams {
   uint32_t inv_P;
   uint32_t stage_bytes, a_off, a_plane_bytes, g_plane_bytes;
   uint32_t tmem_cols;
+  int mma_m;                // 64 when N <= 64 (operand fetch 2 KB instead of 4 KB per MMA: ~1.6x faster), else 128
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
 };
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], done_bar;
   __shared__ uint32_t tmem_base_s;
 
+  pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
   }
   // zero every staging byte once: border slots, slack and the phantom planes read by M = 128 must be finite
   {
-    const uint32_t total16 = (p.stages * p.stage_bytes + (16 - p.g_planes) * p.g_plane_bytes + 4096) >> 4;
+    const uint32_t total16 = (p.stages * p.stage_bytes + (p.mma_m / 8 - p.g_planes) * p.g_plane_bytes + 4096) >> 4;
     for (uint32_t i = tid; i < total16; i += WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
   }
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();      // the prologue above (196 KB of shared-memory zeroing, TMEM allocation) overlapped the previous kernel
 
   if (warp >= 4 && warp < 8) {
     // ===================================== producers ========================================
@@ -193,9 +196,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
     cp_async_wait<0>();
   } else if (warp == 8) {
     // ===================================== MMA issuer =======================================
-    // idesc: FP32 accumulate, BF16 x BF16, A and B both MN-major, N = C, M = 128
+    // idesc: FP32 accumulate, BF16 x BF16, A and B both MN-major, N = C, M = 64 / 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.C >> 3) << 17) |
-                           ((uint32_t)(BM >> 4) << 24);
+                           ((uint32_t)(p.mma_m >> 4) << 24);
     const bool issuer = elect_one();            // one lane issues every MMA and commit of this CTA
     int stage = 0;
     uint32_t phase = 0;
@@ -238,7 +241,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
     // ===================================== final epilogue ====================================
     mbar_wait(&done_bar, 0);
     tc_fence_after();
-    const int n = warp * 32 + lane;              // accumulator row = output channel
+    // accumulator row = output channel.  M = 128: row r lives in TMEM lane r; M = 64: rows 16q .. 16q+15 live in lanes
+    // 32q .. 32q+15 (MEASURED, tools/m64_probe.cu), i.e. the low half of every warp's lane quarter.
+    const int n = (p.mma_m == 64) ? (lane < 16 ? warp * 16 + lane : p.N) : warp * 32 + lane;
     const int TC = p.T * p.C;
     float* dst = p.partial + ((size_t)cta * p.N + n) * TC + (size_t)t0 * p.C;
     const int ncols = ntaps * p.C;
@@ -334,7 +339,8 @@ int wgrad_halo(const WgradParams& p, cudaStream_t st) {
   q.a_plane_bytes = (uint32_t)((R * q.P > (int)slack ? R * q.P : (int)slack) + PAD_SLOTS) * 16;
   q.a_off = (uint32_t)q.g_planes * q.g_plane_bytes;
   q.stage_bytes = (q.a_off + (uint32_t)q.a_planes * q.a_plane_bytes + PAD_SLOTS * 16 + 1023) & ~1023u;
-  const size_t tail = (size_t)(16 - q.g_planes) * q.g_plane_bytes + 4096;   // phantom G planes of the last stage stay inside the allocation
+  q.mma_m = p.N <= 64 ? 64 : 128;
+  const size_t tail = (size_t)(q.mma_m / 8 - q.g_planes) * q.g_plane_bytes + 4096;   // phantom G planes of the last stage stay inside the allocation
   int stages = (int)((200 * 1024 - tail) / q.stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { sv_set_error("wgrad_halo: tile does not fit"); return SV_ERR_UNSUPPORTED; }
@@ -352,7 +358,7 @@ int wgrad_halo(const WgradParams& p, cudaStream_t st) {
       cudaFuncSetAttribute(wgrad_halo_kernel<TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); \
       configured = true;                                                                                   \
     }                                                                                                      \
-    wgrad_halo_kernel<TG><<<grid, WG_THREADS, smem, st>>>(q);                                              \
+    sv_launch_pdl(wgrad_halo_kernel<TG>, dim3(grid), dim3(WG_THREADS), smem, st, q);                                              \
     return sv_check_launch("wgrad_halo");                                                                  \
   }
   SV_WG_CASE(1) SV_WG_CASE(2) SV_WG_CASE(3) SV_WG_CASE(4) SV_WG_CASE(5) SV_WG_CASE(9)

@@ -307,7 +307,7 @@ class Net:
             raw = bytes(arr)
             self._pack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
             self._pack_n = n
-        check(lib.sv_pack_weights_batched(ptr(self._pack_table), self._pack_n, 32, _abi.stream()))
+        check(lib.sv_pack_weights_batched(ptr(self._pack_table), self._pack_n, 592, _abi.stream()))
         return
         st = _abi.stream()
         for pk in self.packs.values():
