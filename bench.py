@@ -117,7 +117,27 @@ def cpu_reference_arm(cfg, steps, warmup, threads=None):
                 ms_per_step=1e3 * tot / steps)
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    chatter from C code) is sent to stderr for the lifetime of the process"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -145,7 +165,7 @@ def main():
                     cpu_baseline=dict(value=r["value"], unit="images/s", cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                     e2e=dict(value=r["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         line["n_gpus"] = world
-        print(json.dumps(line))
+        _emit(line)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (libshotvae has no CPU path)"
@@ -306,7 +326,7 @@ def main():
                           l2="no explicit flush: one step streams ~1.3 GB of saved activations + 150 MB of parameter/optimizer state, > 126 MB L2",
                           last_terms={k: round(v, 4) for k, v in (last or {}).items()},
                           allreduce_bytes_per_step=(reducer.bytes_per_step if reducer else 0))
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
