@@ -46,6 +46,11 @@ EPOCH = 100        # schedules evaluated at a fixed epoch where every loss term 
 BATCH = 128
 
 
+# DRAM bytes per launch of the sv_igemm_fprop family (C2, N=1), from the ncu pass summarised in
+# profiles/r01_launches_n1_summary.md: 11.22 MB against 19.7 MB algorithmic (outputs and re-read inputs stay in L2)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 11.22e6
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured (MEASURED_PEAKS.json)"
@@ -258,6 +263,7 @@ def main():
         net = model._net
         saved = (ts.use_graph, ts.graph)
         saved_reducer, ts.reducer = ts.reducer, None      # rank-0-only replay: no collective (the other ranks are not in it)
+        saved_side, net.side = net.side, None             # one stream: every launch is timed alone, not next to another stream's
         ts.use_graph = False
         ts.run_resident()
         net.timing = []
@@ -271,6 +277,7 @@ def main():
         net.timing = None
         ts.use_graph, ts.graph = saved
         ts.reducer = saved_reducer
+        net.side = saved_side
         agg = {}
         for kind, key, flops, e0, e1, nbytes in recs:
             d = agg.setdefault(kind, dict(ms=0.0, flops=0.0, n=0, bytes=0.0))
@@ -284,7 +291,10 @@ def main():
         step_flops = sum(d["flops"] for d in agg.values()) / 3
         roof = dict(bound="tensor", kernel="sv_igemm_fprop family (conv / convT fprop + dgrad: tcgen05 halo-tile and per-tap TMA kernels, "
                                            "mma.sync for strided / C=16 shapes)",
-                    achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None, peak_source=how + ", sustained bf16",
+                    achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                    traffic_source="dram__bytes_read.sum + dram__bytes_write.sum averaged over the family's launches of one step, "
+                                   "profiles/r01_launches_n1_summary.md (ncu, C2, N=1); algorithmic bytes per launch = "
+                                   "hbm.algorithmic_mb_per_step / launches_per_step", peak_source=how + ", sustained bf16",
                     launches_per_step=f["n"] // 3, avg_launch_us=1e3 * f["ms"] / max(f["n"], 1),
                     algorithmic_gflop_per_step=step_flops / 1e9,
                     hbm=dict(achieved=hbm_ach, peak=hbm_peak, unit="GB/s", frac=(hbm_ach / hbm_peak if hbm_peak else None),

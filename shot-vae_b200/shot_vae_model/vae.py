@@ -51,6 +51,24 @@ class _VAEFunction(torch.autograd.Function):
         cp = pad16(net.in_ch)
         x_img = ctx.t("x_img", (B, 32, 32, cp))
         check(lib.sv_pack_image(ptr(x), ptr(x_img), B, net.in_ch, 32 * 32, cp, st))
+        # model.eval(): BatchNorm uses the running statistics (reference valid()/test(), main_shot_vae.py:414-455);
+        # everything else, including the sampling, is what the reference does in both modes
+        net.eval_bn = not model.training
+        if net.eval_bn and grad_enabled and anchor.requires_grad:
+            net.eval_bn = False
+            model._release_ctx(ctx)
+            raise NotImplementedError("backward through an eval-mode forward is not implemented: wrap it in torch.no_grad() "
+                                      "as the reference's valid()/test() do")
+        try:
+            return _VAEFunction._forward_body(fctx, anchor, model, x, x_img, ctx, mixup, disc_label, disc_pseudo_label, mixup_lam,
+                                              grad_enabled)
+        finally:
+            net.eval_bn = False
+
+    @staticmethod
+    def _forward_body(fctx, anchor, model, x, x_img, ctx, mixup, disc_label, disc_pseudo_label, mixup_lam, grad_enabled):
+        net = model._net
+        B, st = x.size(0), _abi.stream()
         feat = net.encoder_fwd(ctx, x_img)
         mu, ls, la = net.heads_fwd(ctx, feat)
         # host noise, reference order: randn for z first, then rand for the gumbel sample
@@ -213,8 +231,6 @@ class VariationalAutoEncoder(nn.Module):
     def forward(self, input_img, mixup=False, disc_label=None, disc_pseudo_label=None, mixup_lam=None):
         if not input_img.is_cuda:
             raise _abi.ShotVaeError("input must be a CUDA tensor; libshotvae has no CPU path")
-        if not self.training:
-            raise NotImplementedError("eval-mode (running-statistics) forward is outside the training hot path")
         self._ensure_bound()
         return _VAEFunction.apply(self._first, self, input_img, mixup, disc_label, disc_pseudo_label, mixup_lam,
                                   torch.is_grad_enabled())

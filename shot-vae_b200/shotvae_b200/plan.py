@@ -213,6 +213,7 @@ class Net:
             self.b(k).copy_(v.detach().to(self.device))
         self.wg_ws = torch.empty(WG_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
         self.dry = False          # dry mode: build buffers / records only, launch nothing (Ctx views -> parent tape)
+        self.eval_bn = False      # True: BatchNorm normalises with the running statistics (model.eval(), reference valid()/test())
         self.side = None          # optional torch.cuda.Stream for the weight gradients (set by the engine)
         self.timing = None        # bench instrumentation: list of (kind, key, flops, ev0, ev1, algorithmic bytes) when enabled
         self._build_packs()
@@ -402,6 +403,9 @@ class Net:
         ctx.bn[bn_name] = rec
         if self.dry:
             return rec
+        if self.eval_bn:
+            self._bn_eval_coeffs(bn_name, rec)
+            return rec
         check(lib.sv_bn_finalize(ptr(stats), ptr(self.p(bn_name + ".weight")), ptr(self.p(bn_name + ".bias")), float(count),
                                  BN_EPS, G, Cc, Cc, ptr(rec["mean"]), ptr(rec["var"]), ptr(rec["scale"]), ptr(rec["shift"]),
                                  _abi.stream()))
@@ -428,11 +432,25 @@ class Net:
         ctx.bn[bn_name] = rec
         if self.dry:
             return rec
+        if self.eval_bn:
+            self._bn_eval_coeffs(bn_name, rec)
+            self._bn_act(ctx, y, a, rec, slope, count)
+            return rec
         self._timed("bn_fwd_act", key, 4 * y.numel(), lambda: check(lib.sv_bn_finalize_act_fwd(
             ptr(y), ptr(a), ptr(stats), ptr(self.p(bn_name + ".weight")), ptr(self.p(bn_name + ".bias")), float(count), BN_EPS,
             float(slope), count, G, Cc, ptr(rec["mean"]), ptr(rec["var"]), ptr(rec["scale"]), ptr(rec["shift"]), _abi.stream())))
         ctx.bn[bn_name] = rec
         return rec
+
+    def _bn_eval_coeffs(self, bn_name, rec):
+        """eval mode (nn.BatchNorm2d with training=False): scale = gamma / sqrt(running_var + eps), shift = beta -
+        running_mean * scale, the same for every pass group.  Tiny per-channel tensors, outside the training hot path."""
+        Cr = self.p(bn_name + ".weight").numel()
+        rm, rv = self.b(bn_name + ".running_mean"), self.b(bn_name + ".running_var")
+        sc = self.p(bn_name + ".weight") * torch.rsqrt(rv + BN_EPS)
+        for k, v in (("scale", sc), ("shift", self.p(bn_name + ".bias") - rm * sc), ("mean", rm), ("var", rv)):
+            rec[k].zero_()
+            rec[k][:, :Cr] = v
 
     def _bn_act(self, ctx, y, a, rec, slope, rows_per_group):
         check(lib.sv_bn_act_fwd(ptr(y), ptr(a), ptr(rec["scale"]), ptr(rec["shift"]), float(slope), rows_per_group, ctx.G,

@@ -376,3 +376,38 @@ def test_wrn28x10_forward_and_engine_run():
     ts.set_epoch(100)
     t = ts.step(il, ll, iu, lu)
     assert all(np.isfinite(v) for v in t.values()), t
+
+
+@pytest.mark.parametrize("net", ["wideresnet-10-1", "preactresnet18"])
+def test_eval_mode_forward_matches_oracle(net):
+    """model.eval(): BatchNorm normalises with the running statistics and does not update them
+    (the reference's valid()/test(), main_shot_vae.py:414-455)"""
+    from oracle import shotvae_oracle as O
+    nd, B = 10, 8
+    st = O.init_state(net, nd)
+    g = torch.Generator().manual_seed(9)
+    for k in st:                       # non-trivial running statistics
+        if k.endswith("running_mean"):
+            st[k] = 0.2 * torch.randn(st[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            st[k] = 0.5 + torch.rand(st[k].shape, generator=g)
+    il, ll, iu, lu = O.synthetic_batch(B, nd, 13)
+    ost = O.clone_state(st)
+    torch.manual_seed(6)
+    with torch.no_grad():
+        want = O.vae_forward(ost, O.encoder_topology(net), iu, O.LiveDraws(), 0.67, disc_label=lu, training=False)
+    model = build_model(net, nd, st).eval()
+    torch.manual_seed(6)
+    with torch.no_grad():
+        got = model(iu.cuda(), disc_label=lu.cuda())
+    errs = {n: rel(a, b) for n, a, b in zip(("rec", "mu", "ls", "la"), got, want)}
+    _report("forward_eval_%s" % net, errs)
+    assert max(errs.values()) < 3e-2, errs
+    sd = model.state_dict()
+    assert all(torch.equal(sd[k].cpu(), st[k]) for k in st if "running" in k), "eval forward must not touch running statistics"
+    assert all(int(sd[k]) == 0 for k in st if k.endswith("num_batches_tracked"))
+    with pytest.raises(NotImplementedError):      # no backward through an eval-mode forward
+        model(iu.cuda(), disc_label=lu.cuda())
+    model.train()
+    out = model(iu.cuda(), disc_label=lu.cuda())  # and the model still trains afterwards
+    out[1].sum().backward()
