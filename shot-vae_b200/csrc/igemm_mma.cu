@@ -436,21 +436,38 @@ struct PackDesc {
 
 __global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ table) {
   const PackDesc d = table[blockIdx.y];
-  const long long total = (long long)d.T * d.N * d.C;
-  // blocks in proportion to the pack (the 8.4 M-element decoder weight next to 9 K-element 1x1 shortcuts): ~16
-  // elements per thread, the surplus blocks of small packs leave at once
-  const long long want = (total + 256 * 16 - 1) / (256 * 16);
+  // One thread per (output channel n, input channel c) PAIR, all taps in an inner loop: the taps of a pair are
+  // adjacent in the source (OIHW / IOHW weights), so the thread's T reads stay inside one or two 32-byte sectors
+  // (L1 hits after the first) instead of T different threads re-fetching the sector from L2.  The pair index is
+  // decoded so that consecutive threads write consecutive destination elements:
+  //   layout 0  [T][N][C]        : c fastest
+  //   layout 1  [T][C/8][N][8]   : (c % 8) fastest, then n, then c / 8
+  const long long pairs = (long long)d.N * d.C;
+  const long long want = (pairs + 256 * 4 - 1) / (256 * 4);
   const int nblk = (int)(want < (long long)gridDim.x ? want : (long long)gridDim.x);
   if ((int)blockIdx.x >= nblk) return;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)nblk * blockDim.x) {
-    const int c = (int)(i % d.C);
-    const long long r = i / d.C;
-    const int n = (int)(r % d.N);
-    const int t = (int)(r / d.N);
-    float v = 0.f;
-    if (n < d.n_real && c < d.c_real) v = d.src[n * d.sn + c * d.sc + d.tap[t] * d.st];
-    const long long o = d.layout == 0 ? i : ((((long long)t * (d.C >> 3) + (c >> 3)) * d.N + n) << 3) + (c & 7);
-    d.dst[o] = __float2bfloat16(v);
+  const long long NC = (long long)d.N * d.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pairs; i += (long long)nblk * blockDim.x) {
+    int n, c;
+    long long o;           // destination offset of tap 0; taps are NC elements apart in both layouts
+    if (d.layout == 0) {
+      c = (int)(i % d.C);
+      n = (int)(i / d.C);
+      o = i;
+    } else {
+      const int c_lo = (int)(i & 7);
+      const long long r = i >> 3;
+      n = (int)(r % d.N);
+      const int c_hi = (int)(r / d.N);
+      c = c_hi * 8 + c_lo;
+      o = i;               // ((c_hi * N + n) * 8 + c_lo) == i by construction
+    }
+    const bool live = n < d.n_real && c < d.c_real;
+    const float* src = d.src + n * d.sn + c * d.sc;
+    for (int t = 0; t < d.T; ++t) {
+      const float v = live ? src[d.tap[t] * d.st] : 0.f;
+      d.dst[(long long)t * NC + o] = __float2bfloat16(v);
+    }
   }
 }
 
