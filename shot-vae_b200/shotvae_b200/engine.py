@@ -60,6 +60,7 @@ class TrainStep:
         # weight gradients overlap the dgrad / BatchNorm-backward chain on a second stream (SHOTVAE_SIDE=0 turns it off)
         if net.side is None and os.environ.get("SHOTVAE_SIDE", "1") != "0":
             net.side = torch.cuda.Stream(device=net.device)
+        self.side2 = torch.cuda.Stream(device=net.device) if net.side is not None else None
         dev, B, nd, D = net.device, self.B, net.nd, net.ldc
         self.dev = dev
         f32, i64 = torch.float32, torch.int64
@@ -246,13 +247,8 @@ class TrainStep:
             # ---- forward of [P2 | P4]
             featB = net.encoder_fwd(Bc, xB)
             mu2, ls2, la2 = net.heads_fwd(Bc, featB)
-            if not self.skip_dead_decoders:
-                # the reconstructions of P2/P4 are discarded by the reference (main_shot_vae.py:311,356) but
-                # their decoder forwards still update the BatchNorm running statistics
-                with fork():
-                    net.sample_fwd(Bc, 0, 1, self.eps[1], label=self.label_l, label_mix=self.s_lab, lam_dev=self.lam)
-                    latB = net.sample_fwd(Bc, 1, 2, self.eps[3], unif=self.unif[1])
-                    net.decoder_fwd(Bc, latB)
+            # (the decoder forwards of P2/P4 -- kept only for their BatchNorm running statistics -- run beside the
+            # encoder backward in part 1: nothing in the step waits for them before the running-statistics update)
             g_mu2, g_ls2, g_la2 = Bc.t("g.mu", (2 * B, D), torch.float32), Bc.t("g.ls", (2 * B, D), torch.float32), \
                 Bc.t("g.la", (2 * B, nd), torch.float32)
             check(lib.sv_posterior_fwd_bwd(ptr(la2[:B]), None, ptr(self.label_l), ptr(self.s_lab), ptr(self.lam), ptr(mu2[:B]),
@@ -265,9 +261,27 @@ class TrainStep:
         if side is not None:
             main.wait_stream(side)
 
+    def _dead_decoders(self):
+        """decoder forwards of [P2 | P4]: the reference discards these reconstructions (main_shot_vae.py:311,356) but the
+        forwards still update the decoder's BatchNorm running statistics"""
+        net, Bc = self.net, self.ctxB
+        net.sample_fwd(Bc, 0, 1, self.eps[1], label=self.label_l, label_mix=self.s_lab, lam_dev=self.lam)
+        latB = net.sample_fwd(Bc, 1, 2, self.eps[3], unif=self.unif[1])
+        net.decoder_fwd(Bc, latB)
+
     def _part1(self):
         net, A, S = self.net, self.ctxA, self.ctxS
         g_mu, g_ls, g_la = self._g
+        dead = (not self.m2) and (not self.skip_dead_decoders)
+        main = torch.cuda.current_stream()
+        if dead and self.side2 is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side2.wait_event(ev)
+            with torch.cuda.stream(self.side2):
+                self._dead_decoders()
+        elif dead:
+            self._dead_decoders()
         net.sample_bwd(A, 0, self._g_lat, g_mu, g_ls, None, accumulate=1)
         net.sample_bwd(A, 1, self._g_lat, g_mu, g_ls, g_la, accumulate=1)
         if S is not A and not self._adopted:
@@ -277,6 +291,8 @@ class TrainStep:
         D, nd = net.ldc, net.nd
         net.encoder_bwd(S, net.heads_bwd(S, S.t("g.mu", (S.NB, D), torch.float32), S.t("g.ls", (S.NB, D), torch.float32),
                                          S.t("g.la", (S.NB, nd), torch.float32)))
+        if dead and self.side2 is not None:
+            main.wait_stream(self.side2)
 
     def _part2(self):
         net, A, Bc, st = self.net, self.ctxA, self.ctxB, _abi.stream()

@@ -10,7 +10,8 @@ from shotvae_b200.engine import TrainStep
 B, nd = 128, 10
 torch.manual_seed(1)
 model = VariationalAutoEncoder("wideresnet-28-2", 3, 0, (32, 32), False, 128, nd, 0.67, True).cuda().train()
-ts = TrainStep(model, B, hyper=O.default_hyper("Cifar10"), use_graph=False, device_noise=True)
+ts = TrainStep(model, B, hyper=O.default_hyper("Cifar10"), use_graph=False, device_noise=True,
+               skip_dead_decoders=os.environ.get("SKIP_DEAD", "0") == "1")
 ts.set_epoch(100)
 il, ll, iu, lu = O.synthetic_batch(B, nd, 7)
 ts.load_inputs(il, ll, iu, lu)
