@@ -63,6 +63,10 @@ typedef struct {
 int sv_igemm_fprop(const sv_igemm_args* a, void* stream);
 /* 1 if kernel `impl` (1, 2, 3) can run this problem; impl = 0 returns the kernel auto mode selects */
 int sv_igemm_fprop_supports(const sv_igemm_args* a, int32_t impl);
+/* n independent problems (the output-parity phases of one transposed convolution, reference decoder.py:19-63 ->
+ * nn.ConvTranspose2d(k=4, s=2, p=1)).  Up to four problems of identical geometry that run on the per-tap tcgen05
+ * kernel share ONE grid; anything else is launched one after the other.  Same result as n sv_igemm_fprop calls. */
+int sv_igemm_fprop_batch(const sv_igemm_args* args, int32_t n, void* stream);
 
 /* weight-gradient GEMM (replaces the cuDNN wgrad behind every conv / convT backward):
  * part[s][n][t*C + c] = sum over the s-th slice of rows m of  Gr[m, n] * A[gather(m, t), c]

@@ -121,6 +121,30 @@ int sv_igemm_fprop(const sv_igemm_args* a, void* stream) {
   return igemm_fprop_mma(p, st);
 }
 
+int sv_igemm_fprop_batch(const sv_igemm_args* args, int32_t n, void* stream) {
+  SV_REQUIRE(args && n >= 1, "sv_igemm_fprop_batch: no problems");
+#ifndef SV_NO_TCGEN05
+  if (n <= 4) {
+    // one grid when every problem runs on the per-tap tcgen05 kernel with the same geometry
+    IgemmParams ps[4];
+    bool same = true;
+    for (int i = 0; i < n && same; ++i) {
+      if (fill_params(&args[i], ps[i]) != SV_OK) return SV_ERR_ARG;
+      int impl = args[i].impl;
+      if (impl == 0) impl = select_impl(ps[i]);
+      same = impl == 2 && igemm_fprop_tc_supported(ps[i]) && ps[i].NB == ps[0].NB && ps[i].H == ps[0].H && ps[i].W == ps[0].W &&
+             ps[i].C == ps[0].C && ps[i].N == ps[0].N && ps[i].OH == ps[0].OH && ps[i].OW == ps[0].OW;
+    }
+    if (same && n > 1) return igemm_fprop_tc_batch(ps, n, (cudaStream_t)stream);
+  }
+#endif
+  for (int i = 0; i < n; ++i) {
+    const int rc = sv_igemm_fprop(&args[i], stream);
+    if (rc != SV_OK) return rc;
+  }
+  return SV_OK;
+}
+
 static int fill_wgrad(const sv_wgrad_args* a, WgradParams& p) {
   SV_REQUIRE(a && a->A && a->Gr && a->partial, "sv_igemm_wgrad: null operand");
   SV_REQUIRE(a->C % 8 == 0 && a->N % 16 == 0, "sv_igemm_wgrad: C (%d) %% 8, N (%d) %% 16", a->C, a->N);

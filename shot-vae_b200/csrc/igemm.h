@@ -39,6 +39,7 @@ int igemm_wgrad_mma(const WgradParams& p, cudaStream_t st);
 // tcgen05 + TMA path (igemm_tc.cu). Returns SV_ERR_UNSUPPORTED when the shape is not covered.
 bool igemm_fprop_tc_supported(const IgemmParams& p);
 int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st);
+int igemm_fprop_tc_batch(const IgemmParams* ps, int n, cudaStream_t st);   // <= 4 problems of identical tile shape, one grid
 // tcgen05 halo-tile path (igemm_halo.cu)
 bool igemm_fprop_halo_supported(const IgemmParams& p);
 int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st);

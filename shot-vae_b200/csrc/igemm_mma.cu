@@ -484,7 +484,11 @@ extern "C" int sv_pack_weights_batched(const void* table_dev, int32_t n_packs, i
 int igemm_fprop_mma(const IgemmParams& p, cudaStream_t st) {
   const bool k32 = (p.C % 32) == 0;
   const int N = p.N;
+  // long reductions (the decoder's input-gradient GEMMs: K = taps x C up to 4096) are latency bound on the number of
+  // pipeline steps: 64-channel k-blocks halve them
+  const bool k64 = (p.C % 64) == 0 && p.T * p.C >= 1024;
 #define SV_DISPATCH(BNV)                                                     \
+  if (k64) return launch_fprop<BNV, 64>(p, st);                              \
   return k32 ? launch_fprop<BNV, 32>(p, st) : launch_fprop<BNV, 16>(p, st);
   // widest tile that still gives about one CTA per SM: the decoder's input-gradient GEMMs have M = 256 ... 4096
   // rows and K up to 4096, and ran 50-100 us on 16-64 CTAs (latency bound) with the widest tile

@@ -120,8 +120,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
   return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+__device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -354,6 +353,26 @@ int sm_count() {
   return n;
 }
 
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams p) {
+  tc_kernel_body(tmA, tmB, p);
+}
+
+// Up to four independent problems of identical tile shape in ONE grid (blockIdx.y selects the problem): the four
+// output-parity phases of a transposed convolution at 1x1 ... 4x4 resolution are 16-64 CTA GEMMs each, latency
+// bound on their K loop -- side by side they fill the machine instead of running one after the other.
+struct TcBatch {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB[4];
+  TcParams p[4];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc_batched_kernel(const __grid_constant__ TcBatch b) {
+  const int ph = blockIdx.y;
+  tc_kernel_body(b.tmA[ph], b.tmB[ph], b.p[ph]);
+}
+
 }  // namespace
 
 bool igemm_fprop_tc_supported(const IgemmParams& p) {
@@ -371,12 +390,11 @@ bool igemm_fprop_tc_supported(const IgemmParams& p) {
   return get_encode() != nullptr;
 }
 
-int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st) {
+static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtensorMap& tmB, size_t& smem, int& grid) {
   EncodeTiledFn encode = get_encode();
   if (!encode) { sv_set_error("cuTensorMapEncodeTiled unavailable"); return SV_ERR_UNSUPPORTED; }
   TileGeom g;
   if (!tile_geom(p.OH, p.OW, &g)) { sv_set_error("igemm_fprop_tc: unsupported tile geometry"); return SV_ERR_UNSUPPORTED; }
-  TcParams q;
   memset(&q, 0, sizeof(q));
   q.out = p.out; q.res = p.res; q.bias = p.bias; q.stats = p.stats;
   q.M = p.M; q.N = p.N; q.T = p.T;
@@ -404,7 +422,6 @@ int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st) {
   memcpy(q.dx, p.dx, SV_MAX_TAPS);
 
   const CUtensorMapSwizzle sw = q.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.NB};
     cuuint64_t strides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
@@ -423,14 +440,49 @@ int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st) {
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sv_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return SV_ERR_CUDA; }
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(igemm_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = 200 * 1024;
-  }
+  smem = (size_t)stages * stage_bytes + 1024;
   const int total = q.m_tiles * q.n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
+  grid = total < sm_count() ? total : sm_count();
+  return SV_OK;
+}
+
+static void tc_configure() {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(igemm_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(igemm_fprop_tc_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+}
+
+int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st) {
+  TcParams q;
+  CUtensorMap tmA, tmB;
+  size_t smem;
+  int grid;
+  const int rc = tc_setup(p, q, tmA, tmB, smem, grid);
+  if (rc != SV_OK) return rc;
+  tc_configure();
   sv_launch_pdl(igemm_fprop_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, q);
   return sv_check_launch("igemm_fprop_tc");
+}
+
+int igemm_fprop_tc_batch(const IgemmParams* ps, int n, cudaStream_t st) {
+  if (n < 1 || n > 4) { sv_set_error("igemm_fprop_tc_batch: 1..4 problems"); return SV_ERR_ARG; }
+  TcBatch b;
+  memset(&b, 0, sizeof(b));
+  size_t smem = 0;
+  int grid = 0;
+  for (int i = 0; i < n; ++i) {
+    size_t s;
+    int g;
+    const int rc = tc_setup(ps[i], b.p[i], b.tmA[i], b.tmB[i], s, g);
+    if (rc != SV_OK) return rc;
+    if (i > 0 && (s != smem || b.p[i].stages != b.p[0].stages)) { sv_set_error("igemm_fprop_tc_batch: problems differ in tile shape"); return SV_ERR_ARG; }
+    smem = s;
+    if (g > grid) grid = g;
+  }
+  tc_configure();
+  sv_launch_pdl(igemm_fprop_tc_batched_kernel, dim3(grid, n), dim3(TC_THREADS), smem, st, b);
+  return sv_check_launch("igemm_fprop_tc_batch");
 }

@@ -62,6 +62,7 @@ _PROTOS = {
     "sv_sizeof_bn_bwd_term": (C.c_int, []),
     "sv_igemm_fprop": (C.c_int, [C.POINTER(IgemmArgs), vp]),
     "sv_igemm_fprop_supports": (C.c_int, [C.POINTER(IgemmArgs), i32]),
+    "sv_igemm_fprop_batch": (C.c_int, [C.POINTER(IgemmArgs), i32, vp]),
     "sv_igemm_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "sv_igemm_wgrad_splits": (C.c_int, [C.POINTER(WgradArgs)]),
     "sv_wgrad_reduce": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i8p, vp]),

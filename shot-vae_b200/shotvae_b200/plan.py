@@ -317,7 +317,9 @@ class Net:
 
     # ---- low-level launch helpers --------------------------------------------------------------
     def _igemm(self, ctx, key, A, pack, NB, H, W, OH, OW, in_stride=1, out=None, outf=None, res=None, bias=None, stats=None,
-               out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0, exact=False):
+               out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0, exact=False, batch=None):
+        """batch: a list -> the launch is deferred; _igemm_flush(batch) issues all of them through sv_igemm_fprop_batch
+        (independent problems, e.g. the four output-parity phases of a transposed convolution)"""
         a = ctx.args.get(key)
         if a is None:
             pk = self.packs[pack]
@@ -338,6 +340,9 @@ class Net:
         a.impl = 3 if a.w_layout == 1 else (self.impl if self.impl != 3 else 0)
         if self.dry:
             return
+        if batch is not None and self.timing is None:
+            batch.append(a)
+            return
         if self.timing is None:
             check(lib.sv_igemm_fprop(C.byref(a), _abi.stream()))
             return
@@ -351,6 +356,13 @@ class Net:
         nbytes = esz(A) // (in_stride * in_stride) + esz(pk["w"]) + esz(res) + NB * OH * OW * pk["N"] * ((2 if out is not None else 0) +
                                                                                                   (4 if outf is not None else 0))
         self.timing.append(("igemm_fprop", key, flops, e0, e1, nbytes))
+
+    def _igemm_flush(self, batch):
+        if not batch:
+            return
+        arr = (IgemmArgs * len(batch))(*batch)
+        check(lib.sv_igemm_fprop_batch(arr, len(batch), _abi.stream()))
+        del batch[:]
 
     def _wgrad(self, ctx, key, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, wname, n_real, c_real, sn, sc, st, exact=False):
         ent = ctx.args.get(key)
@@ -706,11 +718,13 @@ class Net:
                 yn, stn = ctx.t("rec", (NB, ho, ho, cout), torch.float32), None
             else:
                 yn, stn = ctx.t("d%d.y" % (li + 1), (NB, ho, ho, cout)), ctx.z("d%d.st" % (li + 1), G * 2 * cout)
+            phases = []
             for py in range(2):
                 for px in range(2):
                     self._igemm(ctx, "d%d.f%d%d" % (li + 1, py, px), a, "d%d.f%d%d" % (li + 1, py, px), NB, hin, hin, hin, hin,
                                 out=None if last else yn, outf=yn if last else None, stats=stn, out_stride=2, off=(py, px),
-                                OHf=ho, OWf=ho, n_valid=cout if last else 0, exact=True)
+                                OHf=ho, OWf=ho, n_valid=cout if last else 0, exact=True, batch=phases)
+            self._igemm_flush(phases)     # the four output-parity phases: one grid where the kernel allows it
             y, st, cin, hin = yn, stn, cout, ho
         return y
 

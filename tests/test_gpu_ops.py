@@ -53,7 +53,7 @@ def pack(sv, w, N, Cc, taps, n_real, c_real, sn, sc, st, impl=1):
 
 
 def igemm(sv, A, Wt, taps, NB, H, W, Cc, OH, OW, N, in_stride=1, out=None, outf=None, res=None, bias=None, stats=None,
-          out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0, group_images=None, impl=1):
+          out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0, group_images=None, impl=1, batch=None):
     from shotvae_b200._abi import lib, check, ptr, taps_array, IgemmArgs
     a = IgemmArgs()
     a.A, a.Wt, a.out_bf16, a.out_f32, a.residual, a.bias, a.stats = ptr(A), ptr(Wt), ptr(out), ptr(outf), ptr(res), ptr(bias), ptr(stats)
@@ -66,6 +66,9 @@ def igemm(sv, A, Wt, taps, NB, H, W, Cc, OH, OW, N, in_stride=1, out=None, outf=
     a.w_layout = 1 if impl == 3 else 0
     if impl > 1 and not lib.sv_igemm_fprop_supports(C.byref(a), impl):
         pytest.skip("shape not covered by tcgen05 kernel %d (runs on another kernel)" % impl)
+    if batch is not None:
+        batch.append((a, A, Wt))           # (operands are kept alive with the argument block)
+        return
     check(lib.sv_igemm_fprop(C.byref(a), sv.stream()))
 
 
@@ -115,6 +118,36 @@ def test_convT_fprop_phases_match_torch(sv, impl, cin, cout, Hin, NB):
               n_valid=cout, impl=impl)
     assert rel_rms(from_nhwc(out)[:, :cout], want) < 4e-3
     assert rel_rms(from_nhwc(outf), want) < 1e-3
+
+
+@pytest.mark.parametrize("impl", [0, 2])
+@pytest.mark.parametrize("cin,cout,Hin,NB", [(1024, 512, 1, 16), (512, 256, 2, 8), (256, 128, 4, 8), (128, 64, 8, 4)])
+def test_convT_phases_in_one_grid_equal_separate_launches(sv, impl, cin, cout, Hin, NB):
+    """sv_igemm_fprop_batch: the four output-parity phases in one grid (per-tap tcgen05 kernel) or one after the
+    other (any other kernel) give exactly what four sv_igemm_fprop calls give, statistics included"""
+    from shotvae_b200._abi import lib, check, IgemmArgs
+    from shotvae_b200.plan import dgrad_phase_taps, live_taps
+    torch.manual_seed(cin)
+    x, w = bf(torch.randn(NB, cin, Hin, Hin)), bf(torch.randn(cin, cout, 4, 4) * 0.05)
+    Ho, A = 2 * Hin, nhwc(x)
+    res = []
+    for batched in (False, True):
+        out = torch.zeros(NB, Ho, Ho, cout, dtype=torch.bfloat16, device="cuda")
+        stats = torch.zeros(2, 2, cout, device="cuda")
+        batch = [] if batched else None
+        for (py, px), taps in dgrad_phase_taps(4, 2, 1).items():
+            taps = live_taps(taps, Hin, Hin, Hin, Hin, 1)
+            Wt = pack(sv, w, cout, cin, taps, cout, cin, 16, cout * 16, 1, 1)
+            igemm(sv, A, Wt, taps, NB, Hin, Hin, cin, Hin, Hin, cout, out=out, stats=stats, out_stride=2, off=(py, px), OHf=Ho, OWf=Ho,
+                  group_images=NB // 2, impl=impl, batch=batch)
+        if batched:
+            arr = (IgemmArgs * len(batch))(*[b[0] for b in batch])
+            check(lib.sv_igemm_fprop_batch(arr, len(batch), sv.stream()))
+        torch.cuda.synchronize()
+        res.append((out.float().cpu(), stats.cpu()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert rel_rms(res[1][1], res[0][1]) < 1e-5
+    assert rel_rms(from_nhwc(res[1][0].cuda().to(torch.bfloat16)), F.conv_transpose2d(x, w, None, 2, 1)) < 4e-3
 
 
 @pytest.mark.parametrize("impl", IMPLS)

@@ -336,7 +336,7 @@ def test_engine_graph_replay_equals_eager_sequence():
             draws = (lam_l, torch.randperm(B, generator=g), lam_u, torch.randperm(B, generator=g))
             terms.append(ts.step(il, ll, iu, lu, draws=draws))
         if use_graph:
-            assert ts.graph is not None and ts.launches_per_step > 200
+            assert ts.graph is not None and ts.launches_per_step > 150
         res.append((terms, {k: v.clone() for k, v in model.state_dict().items()}))
     (t0, s0), (t1, s1) = res
     for i, (a, b) in enumerate(zip(t0, t1)):
