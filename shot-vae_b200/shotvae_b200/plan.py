@@ -12,6 +12,7 @@ Design:
     stride-2 input gradients and transposed convolutions are decomposed into output-parity phases.
 """
 import ctypes as C
+import os
 from ctypes import byref
 import math
 import re
@@ -277,8 +278,12 @@ class Net:
                 for (py, px), taps in dgrad_phase_taps(k, s, pad).items():
                     taps = live_taps(taps, hout, hout, hout, hout, 1)
                     if taps:
+                        # 128 -> 128 channels at 8x8: the halo kernel has to split N into two 64-column halves (295 KB of
+                        # weights) and half of every 128-slot tile is padding; without an epilogue to fuse, the per-tap kernel
+                        # with whole-N tiles is faster there (MEASURED: 18 vs 23 us at NB = 256)
+                        big = ci >= 128 and co >= 128 and s == 1 and k == 3 and os.environ.get("SHOTVAE_B3_DGRAD", "tc") == "tc"
                         self._add_pack("u%d.%s.d%d%d" % (ui, cname, py, px), wname, ci, co, taps, ci, co, K, ci * K, 1,
-                                       grid=(hout, hout))
+                                       grid=None if big else (hout, hout))
             H = Ho
         # decoder: ConvTranspose2d weights are [Cin, Cout, k, k]
         cin, hin = DEC_CHANNELS[0], 1
