@@ -147,41 +147,6 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-// 16 values per lane (one row each) -> lane j (< 16) of each half-warp pair ends with the column sums.
-// Butterfly transpose-reduce over the 32 lanes: 16 columns => 8+4+2+1 exchanges + 1 final fold.
-__device__ __forceinline__ float colsum16(const float* v, int lane) {
-  float a[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 8;
-    const float send = up ? v[i] : v[i + 8];
-    const float keep = up ? v[i + 8] : v[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 4;
-    const float send = up ? a[i] : a[i + 4];
-    const float keep = up ? a[i + 4] : a[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 2;
-    const float send = up ? a[i] : a[i + 2];
-    const float keep = up ? a[i + 2] : a[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  {
-    const bool up = lane & 1;
-    const float send = up ? a[0] : a[1];
-    const float keep = up ? a[1] : a[0];
-    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  // lanes L and L^16 hold partial sums of the same column (L & 15): fold the two half warps
-  return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16);
-}
-
 template <int T_, int KC_>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 igemm_halo_kernel(const HaloParams p) {

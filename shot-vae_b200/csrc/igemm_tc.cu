@@ -259,14 +259,14 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
         }
         if (p.stats != nullptr) {
+          // 16 columns x 32 rows -> per-column sums by a butterfly transpose-reduce (20 shuffles instead of 160)
+          float sq[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float s1 = warp_sum(v[j]);
-            const float s2 = warp_sum(v[j] * v[j]);
-            if (lane == j) {
-              atomicAdd(&s_stat[g][0][c0 + j], s1);
-              atomicAdd(&s_stat[g][1][c0 + j], s2);
-            }
+          for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+          const float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
+          if (lane < 16) {
+            atomicAdd(&s_stat[g][0][c0 + lane], s1);
+            atomicAdd(&s_stat[g][1][c0 + lane], s2);
           }
         }
       }

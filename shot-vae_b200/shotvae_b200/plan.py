@@ -273,15 +273,15 @@ class Net:
                 wname = u.prefix + (".i_block.conv.weight" if cname == "sc" else ".f_block.%s.weight" % cname)
                 K = k * k
                 hout = hin // s
+                # 128 -> 128 channels at 8x8: the halo kernel has to split N into two 64-column halves (295 KB of weights) and
+                # half of every 128-slot tile is padding; the per-tap kernel with whole-N tiles is faster there
+                # (MEASURED at NB = 256: 16.6 vs 23.1 us plain, 19.1 vs 24.0 us with residual + statistics)
+                big = ci >= 128 and co >= 128 and s == 1 and k == 3 and os.environ.get("SHOTVAE_B3", "tc") == "tc"
                 self._add_pack("u%d.%s.f" % (ui, cname), wname, co, ci, conv_taps(k, pad), co, ci, ci * K, K, 1,
-                               grid=(hin, hin) if s == 1 else None)
+                               grid=(hin, hin) if (s == 1 and not big) else None)
                 for (py, px), taps in dgrad_phase_taps(k, s, pad).items():
                     taps = live_taps(taps, hout, hout, hout, hout, 1)
                     if taps:
-                        # 128 -> 128 channels at 8x8: the halo kernel has to split N into two 64-column halves (295 KB of
-                        # weights) and half of every 128-slot tile is padding; without an epilogue to fuse, the per-tap kernel
-                        # with whole-N tiles is faster there (MEASURED: 18 vs 23 us at NB = 256)
-                        big = ci >= 128 and co >= 128 and s == 1 and k == 3 and os.environ.get("SHOTVAE_B3_DGRAD", "tc") == "tc"
                         self._add_pack("u%d.%s.d%d%d" % (ui, cname, py, px), wname, ci, co, taps, ci, co, K, ci * K, 1,
                                        grid=None if big else (hout, hout))
             H = Ho
