@@ -47,8 +47,8 @@ BATCH = 128
 
 
 # DRAM bytes per launch of the sv_igemm_fprop family (C2, N=1), from the ncu pass summarised in
-# profiles/r01_launches_n1_summary.md: 11.22 MB against 19.7 MB algorithmic (outputs and re-read inputs stay in L2)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 11.22e6
+# profiles/r01_launches_n1_summary.md: 14.02 MB against 19.7 MB algorithmic (outputs and re-read inputs stay in L2)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 14.02e6
 
 
 def peaks():
