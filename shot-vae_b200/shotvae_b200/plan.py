@@ -668,14 +668,27 @@ class Net:
         g_logits = ctx.t("g.logits", (NB, self.nd), torch.float32)
         check(lib.sv_log_softmax_bwd(ptr(g_la), ptr(ctx.bufs["la"]), ptr(g_logits), NB, self.nd, s))
         g_feat = ctx.t("g.feat", (NB, Cf), torch.float32)
-        first = True
-        for (hname, short), g in zip(self.HEADS, (g_mu, g_ls, g_logits)):
-            n = self.nd if short == "logits" else self.ldc
-            check(lib.sv_linear_bwd_weight(ptr(g), None, n, ptr(ctx.feat), Cf, ptr(self.g(hname + ".fc.weight")), Cf, 0,
-                                           ptr(self.g(hname + ".fc.bias")), NB, n, Cf, s))
+        heads = [(hname, self.nd if short == "logits" else self.ldc, g) for (hname, short), g in zip(self.HEADS, (g_mu, g_ls, g_logits))]
+
+        def weight_grads():
+            for hname, n, g in heads:
+                check(lib.sv_linear_bwd_weight(ptr(g), None, n, ptr(ctx.feat), Cf, ptr(self.g(hname + ".fc.weight")), Cf, 0,
+                                               ptr(self.g(hname + ".fc.bias")), NB, n, Cf, _abi.stream()))
+
+        # the head weight gradients are not needed by the backward chain: side stream (joined at the end of encoder_bwd,
+        # which always follows)
+        side = self.side if not self.dry else None
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                weight_grads()
+        else:
+            weight_grads()
+        for i, (hname, n, g) in enumerate(heads):
             check(lib.sv_linear_bwd_input(ptr(g), None, n, ptr(self.p(hname + ".fc.weight")), Cf, 0, ptr(g_feat), Cf,
-                                          0 if first else 1, NB, n, Cf, s))
-            first = False
+                                          0 if i == 0 else 1, NB, n, Cf, s))
         return g_feat
 
     def sample_fwd(self, ctx, group, mode, eps, unif=None, label=None, label_mix=None, lam_dev=None):
