@@ -3,12 +3,12 @@
 //
 // The 3x3 (or 1x1 / 2x2-phase) convolution over an H x W image is evaluated in "slot space": the
 // image is viewed with a one-pixel zero border, pitch P = W + 2, slot = y*P + x.  A tile is 128
-// consecutive output slots.  One TMA load brings the R padded rows that the tile and its halo touch
+// consecutive output slots.  Producer warps bring the R padded rows that the tile and its halo touch
 // into shared memory in the NO-SWIZZLE K-major canonical layout ("interleaved": planes of 8 channels,
 // consecutive slots 16 bytes apart).  In that layout the operand for tap (dy, dx) is the SAME buffer
 // read from a start address shifted by (dy*P + dx) slots, so each tap is just a different UMMA shared
 // memory descriptor: 9 taps x C/16 MMAs per tile, zero data movement between taps.  Out-of-image
-// elements are zero-filled by the TMA unit (that is the padding); the two border slots per row produce
+// rows are zero-filled by the copies (that is the padding); the two border slots per row produce
 // garbage accumulator rows that the epilogue simply does not store.
 //
 // The weights of all taps for this CTA's output-channel slice stay resident in shared memory (same
@@ -16,9 +16,11 @@
 //
 // Measured on B200: the TMA unit retires roughly one innermost box row per ~5 cycles whatever its
 // length, so a tensor-map load with 16-byte rows (what the interleaved layout needs) is ~10x too slow.
-// The A tile is therefore staged by four producer warps with zero-filling 16-byte cp.async (global
+// The A tile is therefore staged by three producer warps with zero-filling 16-byte cp.async (global
 // reads fully coalesced: one image row = W*C*2 contiguous bytes), published to the tensor core with
-// fence.proxy.async + mbarrier; the resident weights arrive by 1-D bulk copies (cp.async.bulk).
+// cp.async.mbarrier.arrive.noinc + a consumer-side fence.proxy.async; the resident weights arrive by 1-D bulk
+// copies (cp.async.bulk).  The staged (shared memory + bulk store) epilogue behind SHOTVAE_HALO_STAGE=1 is an
+// experiment that measured slower than the direct 32-byte stores and is off by default.
 //
 // warp roles (12 warps = 3 per scheduler, so every thread may use 168 registers): 0..3 and 8..11 = epilogue
 // (TMEM -> registers -> +bias/+residual -> bf16 NHWC 32-byte stores, BatchNorm sum / sum^2), 4..6 = A-tile
