@@ -127,3 +127,19 @@ def test_convT_phase_tables_reproduce_conv_transpose(Hin):
     w_tap = torch.stack([w[:, :, t[0] // 4, t[0] % 4] for t in taps])               # [T][n=ci][c=co]
     gin = _gather_conv(g, w_tap, taps, Hin, Hin, 2, 1, (0, 0), Hin, Hin)
     assert torch.allclose(gin, x.grad, atol=1e-10)
+
+
+def test_product_package_never_imports_the_oracle():
+    """the oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use it"""
+    import re
+    pkg = os.path.join(ROOT, "shot-vae_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        if os.sep + "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "shotvae_oracle" in txt:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
