@@ -355,10 +355,16 @@ class TrainStep:
     def load_inputs(self, image_l, label_l, image_u, label_u, draws="auto"):
         """host -> device copy of one (labelled, unlabelled) batch pair through pinned staging buffers,
         plus the host RNG draws of this step"""
-        self.h_img_l.copy_(image_l); self.h_img_u.copy_(image_u)
+        # images that already sit in pinned host memory are copied straight from there (the caller must leave them
+        # untouched until the step has been synchronised -- step() does that before it returns); anything else goes
+        # through the pinned staging buffers
+        for dst, staged, src in ((self.img_l, self.h_img_l, image_l), (self.img_u, self.h_img_u, image_u)):
+            if src.device.type == "cpu" and src.is_pinned() and src.dtype == dst.dtype and src.shape == dst.shape and src.is_contiguous():
+                dst.copy_(src, non_blocking=True)
+            else:
+                staged.copy_(src)
+                dst.copy_(staged, non_blocking=True)
         self.h_label_l.copy_(label_l); self.h_label_u.copy_(label_u)
-        self.img_l.copy_(self.h_img_l, non_blocking=True)
-        self.img_u.copy_(self.h_img_u, non_blocking=True)
         self.label_l.copy_(self.h_label_l, non_blocking=True)
         self.label_u.copy_(self.h_label_u, non_blocking=True)
         self.stage_draws(self.draw_host() if draws == "auto" else draws, self.h_label_l)
