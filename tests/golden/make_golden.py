@@ -155,6 +155,48 @@ def run_case(M, case):
     return g
 
 
+def eval_state(O, net, nd, seed):
+    """constructor-initialised state with non-trivial BatchNorm running statistics (shared with the tests)"""
+    st = O.init_state(net, nd)
+    g = torch.Generator().manual_seed(seed)
+    for k in st:
+        if k.endswith("running_mean"):
+            st[k] = 0.2 * torch.randn(st[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            st[k] = 0.5 + torch.rand(st[k].shape, generator=g)
+    return st
+
+
+def run_eval_case(M, case):
+    """the reference MODULE in eval mode (what its valid()/test() call, main_shot_vae.py:414-455): BatchNorm with
+    running statistics, sampling unchanged"""
+    sys.path.insert(0, ROOT)
+    from oracle import shotvae_oracle as O
+    net, nd, batch = case["net"], case["nd"], case["batch"]
+    model = M.VariationalAutoEncoder(encoder_name=net, num_input_channels=3, drop_rate=0, img_size=(32, 32),
+                                     data_parallel=False, continuous_latent_dim=128, disc_latent_dim=nd,
+                                     sample_temperature=0.67, small_input=True)
+    st = eval_state(O, net, nd, case["state_seed"])
+    model.load_state_dict(st)
+    model.eval()
+    il, ll, iu, lu = O.synthetic_batch(batch, nd, case["data_seed"])
+    g = dict(case=case, outputs={})
+    with torch.no_grad():
+        torch.manual_seed(case["rng_seed"])
+        out = model(iu, disc_label=lu)                      # labelled form (one-hot y)
+        g["outputs"]["with_label"] = [summarize(t) for t in out]
+        torch.manual_seed(case["rng_seed"])
+        out = model(iu)                                     # gumbel-softmax form
+        g["outputs"]["gumbel"] = [summarize(t) for t in out]
+    after = model.state_dict()
+    g["running_stats_untouched"] = bool(all(torch.equal(after[k], st[k]) for k in st))
+    return g
+
+
+CASES_EVAL = [
+    dict(name="eval_wrn28x2_nd10_b16", net="wideresnet-28-2", nd=10, batch=16, data_seed=31, rng_seed=12, state_seed=9),
+    dict(name="eval_preact18_nd10_b8", net="preactresnet18", nd=10, batch=8, data_seed=32, rng_seed=13, state_seed=9),
+]
 CASES_SHOT = [
     dict(name="c2_wrn28x2_nd10_b16_e100", net="wideresnet-28-2", nd=10, batch=16, epoch=100, om=False, m2=False, data_seed=11, rng_seed=5),
     dict(name="c2_wrn28x2_nd10_b128_e0", net="wideresnet-28-2", nd=10, batch=128, epoch=0, om=False, m2=False, data_seed=12, rng_seed=6),
@@ -171,13 +213,21 @@ CASES_M2 = [
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "shot"
-    if which == "shot":
+    if which in ("shot", "eval"):
         M = import_reference("main_shot_vae", ["main_shot_vae.py", "--gpu", "", "--dp", "--br", "-b", "128"])
         cases = CASES_SHOT
     else:
         M = import_reference("main_M2_vae", ["main_M2_vae.py", "--gpu", "", "--dp", "-b", "128",
                                              "--net-name", "preactresnet18", "--dataset", "Cifar100"])
         cases = CASES_M2
+    if which in ("shot", "eval"):
+        for case in CASES_EVAL:
+            g = run_eval_case(M, case)
+            with open(os.path.join(HERE, case["name"] + ".json"), "w") as f:
+                json.dump(g, f)
+            print(case["name"], "running stats untouched:", g["running_stats_untouched"])
+    if which == "eval":
+        return
     for case in cases:
         g = run_case(M, case)
         with open(os.path.join(HERE, case["name"] + ".json"), "w") as f:

@@ -384,13 +384,8 @@ def test_eval_mode_forward_matches_oracle(net):
     (the reference's valid()/test(), main_shot_vae.py:414-455)"""
     from oracle import shotvae_oracle as O
     nd, B = 10, 8
-    st = O.init_state(net, nd)
-    g = torch.Generator().manual_seed(9)
-    for k in st:                       # non-trivial running statistics
-        if k.endswith("running_mean"):
-            st[k] = 0.2 * torch.randn(st[k].shape, generator=g)
-        elif k.endswith("running_var"):
-            st[k] = 0.5 + torch.rand(st[k].shape, generator=g)
+    from tests.golden.make_golden import eval_state
+    st = eval_state(O, net, nd, 9)          # non-trivial running statistics (the state of the eval goldens)
     il, ll, iu, lu = O.synthetic_batch(B, nd, 13)
     ost = O.clone_state(st)
     torch.manual_seed(6)

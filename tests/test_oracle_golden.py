@@ -12,7 +12,9 @@ import torch
 from oracle import shotvae_oracle as O
 from tests.golden.make_golden import sample_positions
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.json")))
+_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.json")))
+GOLD = [p for p in _ALL if not os.path.basename(p).startswith("eval_")]
+GOLD_EVAL = [p for p in _ALL if os.path.basename(p).startswith("eval_")]
 RTOL = 1e-5
 
 
@@ -70,3 +72,25 @@ def test_oracle_matches_reference_golden(path):
     O.sgd_step(st, {}, lr=0.1)
     for k, gs in g["post_state"].items():
         check_summary(st[k].float(), gs, "state " + k, rtol=1e-4)
+
+
+@pytest.mark.parametrize("path", GOLD_EVAL, ids=[os.path.basename(p)[:-5] for p in GOLD_EVAL])
+def test_oracle_eval_forward_matches_reference_module(path):
+    """model.eval() forward of the reference module (BatchNorm on running statistics; what valid()/test() run,
+    main_shot_vae.py:414-455) against the oracle's training=False path"""
+    from tests.golden.make_golden import eval_state
+    g = json.load(open(path))
+    c = g["case"]
+    assert g["running_stats_untouched"]
+    st = eval_state(O, c["net"], c["nd"], c["state_seed"])
+    il, ll, iu, lu = O.synthetic_batch(c["batch"], c["nd"], c["data_seed"])
+    topo = O.encoder_topology(c["net"])
+    with torch.no_grad():
+        torch.manual_seed(c["rng_seed"])
+        out = O.vae_forward(st, topo, iu, O.LiveDraws(), 0.67, disc_label=lu, training=False)
+        for t, gs, n in zip(out, g["outputs"]["with_label"], ("rec", "mu", "ls", "la")):
+            check_summary(t, gs, "eval/with_label/" + n)
+        torch.manual_seed(c["rng_seed"])
+        out = O.vae_forward(st, topo, iu, O.LiveDraws(), 0.67, training=False)
+        for t, gs, n in zip(out, g["outputs"]["gumbel"], ("rec", "mu", "ls", "la")):
+            check_summary(t, gs, "eval/gumbel/" + n)
