@@ -204,6 +204,8 @@ CASES_SHOT = [
     dict(name="c3_wrn28x2_nd100_b16_e100_mse", net="wideresnet-28-2", nd=100, batch=16, epoch=100, om=False, m2=False, br=False, data_seed=14, rng_seed=8),
     dict(name="wrn10x1_nd10_b8_e100", net="wideresnet-10-1", nd=10, batch=8, epoch=100, om=False, m2=False, data_seed=15, rng_seed=9),
     dict(name="preact18_shot_nd10_b8_e100", net="preactresnet18", nd=10, batch=8, epoch=100, om=False, m2=False, data_seed=16, rng_seed=10),
+    dict(name="c2_wrn28x2_nd10_b16_e0_seed2", net="wideresnet-28-2", nd=10, batch=16, epoch=0, om=False, m2=False, data_seed=2, rng_seed=2),
+    dict(name="c3_wrn28x2_nd100_b16_e400_seed3", net="wideresnet-28-2", nd=100, batch=16, epoch=400, om=False, m2=False, data_seed=3, rng_seed=3),
 ]
 CASES_M2 = [
     dict(name="c5_m2_preact18_nd100_b16_e100", net="preactresnet18", nd=100, batch=16, epoch=100, om=False, m2=True, br=False, data_seed=21, rng_seed=3),
@@ -213,6 +215,7 @@ CASES_M2 = [
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "shot"
+    only = sys.argv[2] if len(sys.argv) > 2 else None      # optional: regenerate one case by name (read before argv is patched)
     if which in ("shot", "eval"):
         M = import_reference("main_shot_vae", ["main_shot_vae.py", "--gpu", "", "--dp", "--br", "-b", "128"])
         cases = CASES_SHOT
@@ -220,7 +223,7 @@ def main():
         M = import_reference("main_M2_vae", ["main_M2_vae.py", "--gpu", "", "--dp", "-b", "128",
                                              "--net-name", "preactresnet18", "--dataset", "Cifar100"])
         cases = CASES_M2
-    if which in ("shot", "eval"):
+    if which == "eval" or (which == "shot" and not only):
         for case in CASES_EVAL:
             g = run_eval_case(M, case)
             with open(os.path.join(HERE, case["name"] + ".json"), "w") as f:
@@ -229,6 +232,8 @@ def main():
     if which == "eval":
         return
     for case in cases:
+        if only and case["name"] != only:
+            continue
         g = run_case(M, case)
         with open(os.path.join(HERE, case["name"] + ".json"), "w") as f:
             json.dump(g, f)
