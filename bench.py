@@ -181,7 +181,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from shot_vae_model.vae import VariationalAutoEncoder
     from shotvae_b200.engine import TrainStep, default_hyper
-    from shotvae_b200 import _abi
+    from shotvae_b200 import _abi          # noqa: F401  (loads libshotvae.so: fails loudly here if the extension is missing)
     from shotvae_b200.ddp import GradReducer
 
     log = lambda m: print("[bench rank %d] %s" % (rank, m), file=sys.stderr, flush=True)

@@ -14,7 +14,6 @@ Design:
 import ctypes as C
 import os
 from ctypes import byref
-import math
 import re
 from collections import OrderedDict
 
@@ -314,11 +313,6 @@ class Net:
             self._pack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
             self._pack_n = n
         check(lib.sv_pack_weights_batched(ptr(self._pack_table), self._pack_n, 592, _abi.stream()))
-        return
-        st = _abi.stream()
-        for pk in self.packs.values():
-            check(lib.sv_pack_weight(ptr(self.p(pk["wname"])), ptr(pk["w"]), pk["N"], pk["C"], pk["T"], pk["n_real"],
-                                     pk["c_real"], pk["sn"], pk["sc"], pk["st"], pk["tidx"], pk["layout"], st))
 
     # ---- low-level launch helpers --------------------------------------------------------------
     def _igemm(self, ctx, key, A, pack, NB, H, W, OH, OW, in_stride=1, out=None, outf=None, res=None, bias=None, stats=None,
