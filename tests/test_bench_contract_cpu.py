@@ -42,3 +42,12 @@ def test_committed_gpu_line_has_the_contract_keys():
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and not d["clocks"]["reasons"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "images/s" and cb["value"] > 0
+
+
+def test_launch_summary_reads_the_committed_ncu_list():
+    """profiles/r01_launches_n1.csv (ncu launch list of three steady-state steps) -> per-family table"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), os.path.join(ROOT, "profiles", "r01_launches_n1.csv"),
+                        "357"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    assert "3.00 steps of 357 launches" in r.stdout
+    assert "conv fprop/dgrad (sv_igemm_fprop)" in r.stdout and "BatchNorm backward" in r.stdout
