@@ -230,6 +230,34 @@ int sv_pairwise_kl_second_nearest(const float* mu, const float* ls, int32_t B, i
  * {lr, momentum, wd, grad_scale, first_step_flag}. */
 int sv_sgd_step(float* param, float* grad, float* momentum_buf, const float* hyper, int64_t n, void* stream);
 
+/* ---- entry points the reference defines but never calls on the training path -----------
+ * Pairwise distances of lib/utils/calculate_dist.py:94-160: out[i][j] fp32 [n1][n2] between rows of (u1, ls1)
+ * [n1][D] and (u2, ls2) [n2][D]; ls operands may be NULL for SV_DIST_SQ_EUCLID / SV_DIST_COSINE. */
+#define SV_DIST_GAUSSIAN_KL 0   /* pairwise_norm_kl_dist_gpu (:94-107): KL(N(u1_i, e^ls1_i) || N(u2_j, e^ls2_j)) */
+#define SV_DIST_SQ_EUCLID 1     /* pairwise_square_euclidean_gpu (:110-117) */
+#define SV_DIST_WASSERSTEIN 2   /* pairwise_norm_wasserstein_dist_gpu (:120-130) */
+#define SV_DIST_COSINE 3        /* calculate_mean_dist_pairwise(distance="cosine") (:146-149), norms squared as written */
+int sv_pairwise_dist(const float* u1, const float* ls1, const float* u2, const float* ls2, int32_t n1, int32_t n2, int32_t D,
+                     int32_t mode, float* out, void* stream);
+/* Two-distribution forms of KLNormCriterion / KLDiscCriterion (lib/criterion.py:151-157,172-176): *loss += sum/batch
+ * (loss must be zeroed by the caller), g0..g3 (optional) receive d loss / d x0..x3.
+ * SV_KLPAIR_NORM: x0 = mean_pre, x1 = log_sigma_pre, x2 = mean_gt, x3 = sigma_gt;
+ * SV_KLPAIR_DISC_QP / _PQ: x0 = log q (prediction), x1 = p (target probabilities), x2 = x3 = NULL. */
+#define SV_KLPAIR_NORM 0
+#define SV_KLPAIR_DISC_QP 1
+#define SV_KLPAIR_DISC_PQ 2
+int sv_kl_pair_fwd_bwd(int32_t mode, const float* x0, const float* x1, const float* x2, const float* x3, int64_t n, int32_t batch,
+                       float* loss, float* g0, float* g1, float* g2, float* g3, void* stream);
+
+/* ---- device input pipeline (lib/dataloader.py:42-70: Pad(4, reflect) -> RandomHorizontalFlip -> RandomCrop(32)
+ *      -> ToTensor) over a device-resident uint8 dataset ------------------------------------------------------
+ * data: uint8 [n_images][src_h][src_w][ch] (src_hwc = 1: CIFAR / MNIST storage) or [n_images][ch][src_h][src_w]
+ * (src_hwc = 0: SVHN storage); index (optional) int64 [B] selects the images; params (optional) int32 [B][3] =
+ * {crop row i, crop column j, flip} with i, j in [0, src + 2*pad - out] (NULL: no augmentation, i = j = flip = 0).
+ * out: fp32 NCHW [B][ch][out_h][out_w] in [0, 1], bit-exact with torchvision (uint8 / 255 in fp32). */
+int sv_augment_batch(const uint8_t* data, const int64_t* index, const int32_t* params, int32_t B, int32_t ch, int32_t src_h,
+                     int32_t src_w, int32_t pad, int32_t out_h, int32_t out_w, int32_t src_hwc, float* out, void* stream);
+
 /* debugging aid: per-tile clock64 stamps of CTA 0 of the last halo-kernel launch run with
  * SHOTVAE_HALO_TRACE=1 ([role: producer, mma, mma-acc-wait, epilogue][tile < 64][begin, end]) */
 int sv_debug_halo_trace(long long* host_out);

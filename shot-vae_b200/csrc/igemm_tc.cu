@@ -13,14 +13,21 @@
 // * epilogue (4 warps): tcgen05.ld -> +bias, +residual -> bf16 NHWC store (any output stride: serves
 //   transposed-conv / strided-dgrad phases) and per-channel sum / sum^2 for the next BatchNorm.
 //
-// warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+// warp roles: 1 = MMA issuer, 4..7 = epilogue, 0 / 2 / 3 / 8 / 9 / 10 = TMA producers (2 also allocates TMEM).
+//
+// MEASURED (tools/tma_probe.cu, profiles/r02_kernel_findings.md): tensor-map loads issued by ONE thread do not
+// overlap -- each costs a full ~700-cycle round trip whatever the box size (4 KB or 32 KB) and however many
+// stages are free, i.e. 23 B/cycle/SM for 16 KB boxes -- while loads issued from different warps run in parallel
+// (2 issuers: 47, 4 issuers: 72 B/cycle/SM = the L2 fabric limit).  The A and B loads of consecutive k-blocks are
+// therefore dealt round-robin to six producer warps; a stage's full barrier counts two arrivals (A and B).
 #include <cuda.h>
 #include "common.cuh"
 #include "igemm.h"
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;
+constexpr int N_PRODUCERS = 6;
 constexpr int BM = 128;
 constexpr int MAX_GROUPS = 4;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
@@ -124,7 +131,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_stat[MAX_GROUPS][2][128];
+  __shared__ float s_stat[MAX_GROUPS][2][256];
 
   pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31;
@@ -134,14 +141,14 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
   const uint32_t stage_bytes = (a_bytes + b_bytes + 1023) & ~1023u;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int KT = p.T * p.KC;
-  const uint32_t tmem_cols = p.BN <= 32 ? 64 : (p.BN <= 64 ? 128 : 256);   // two accumulator stages
+  const uint32_t tmem_cols = p.BN <= 32 ? 64 : (p.BN <= 64 ? 128 : (p.BN <= 128 ? 256 : 512));   // two accumulator stages
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < MAX_GROUPS * 2 * 128; i += TC_THREADS) (&s_stat[0][0][0])[i] = 0.f;
+  for (int i = tid; i < MAX_GROUPS * 2 * 256; i += TC_THREADS) (&s_stat[0][0][0])[i] = 0.f;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols)
                  : "memory");
@@ -153,24 +160,36 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
 
-  if (warp == 0 && lane == 0) {
-    // ===================================== TMA producer =====================================
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int img0 = (mt / p.tiles_h) * p.Nt;
-      const int h0 = (mt % p.tiles_h) * p.Ht;
-      for (int kb = 0; kb < KT; ++kb) {
-        const int t = kb / p.KC, cb = kb - t * p.KC;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-        mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-        tma_load_4d(sa, &tmA, &full_bar[stage], cb * p.KB, (int)p.dx[t], h0 + (int)p.dy[t], img0);
-        tma_load_3d(sa + a_bytes, &tmB, &full_bar[stage], cb * p.KB, nt * p.BN, t);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+  const int prod = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : (warp >= 8 && warp <= 10 ? warp - 5 : -1)));
+  if (prod >= 0) {
+    // ===================================== TMA producers =====================================
+    // load number 2*g is the A tile of global k-block g, 2*g + 1 its B tile; producer `prod` issues the loads
+    // whose number is congruent to it mod N_PRODUCERS
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      int g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const int img0 = (mt / p.tiles_h) * p.Nt;
+        const int h0 = (mt % p.tiles_h) * p.Ht;
+        for (int kb = 0; kb < KT; ++kb, ++g) {
+          const int la = (2 * g) % N_PRODUCERS;
+          const bool do_a = la == prod, do_b = (la + 1) % N_PRODUCERS == prod;
+          if (!do_a && !do_b) continue;
+          const int t = kb / p.KC, cb = kb - t * p.KC;
+          const int stage = g % p.stages;
+          mbar_wait(&empty_bar[stage], (uint32_t)(((g / p.stages) & 1) ^ 1));
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          if (do_a) {
+            mbar_expect_tx(&full_bar[stage], a_bytes);
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * p.KB, (int)p.dx[t], h0 + (int)p.dy[t], img0);
+          }
+          if (do_b) {
+            mbar_expect_tx(&full_bar[stage], b_bytes);
+            tma_load_3d(sa + a_bytes, &tmB, &full_bar[stage], cb * p.KB, nt * p.BN, t);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -210,7 +229,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===================================== epilogue ==========================================
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     int acc = 0;
@@ -375,13 +394,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc_batched_kernel(c
 
 }  // namespace
 
+// channel tile: whole N up to 128; beyond that the largest multiple of 16 that divides N and fits one MMA (<= 256)
+// whose tile still leaves >= 4 shared-memory stages (160 for N = 160 / 320, 128 for N = 256 / 512 / 640)
+static int pick_bn(int N) {
+  if (N <= 128) return N;
+  if (N % 128 == 0) return 128;
+  for (int bn = 192; bn >= 64; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
 bool igemm_fprop_tc_supported(const IgemmParams& p) {
   TileGeom g;
   if (p.w_layout != 0) return false;
   if (p.in_stride != 1 || p.H != p.OH || p.W != p.OW) return false;
   if (!tile_geom(p.OH, p.OW, &g)) return false;
   if (p.C % 32 != 0 || p.N % 16 != 0) return false;
-  if (p.N > 128 && p.N % 128 != 0) return false;
+  if (pick_bn(p.N) == 0) return false;
   if (p.out == nullptr || p.outf != nullptr) return false;
   if (p.stats != nullptr && (p.rows_per_group % BM != 0 || p.NB / p.group_images > MAX_GROUPS)) return false;
   if (p.NB < g.Nt) return false;
@@ -398,16 +427,18 @@ static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtenso
   memset(&q, 0, sizeof(q));
   q.out = p.out; q.res = p.res; q.bias = p.bias; q.stats = p.stats;
   q.M = p.M; q.N = p.N; q.T = p.T;
-  q.KB = (p.C % 64 == 0) ? 64 : 32;
-  q.KC = p.C / q.KB;
+  // 64-channel k-blocks (128-byte swizzled rows); a ragged last block (C = 160: 64 + 64 + 32) reads out of
+  // bounds along the channel dimension of BOTH tensor maps, which TMA fills with zeros
+  q.KB = p.C >= 64 ? 64 : 32;
+  q.KC = ceil_div(p.C, q.KB);
   q.OH = p.OH; q.OW = p.OW; q.OHf = p.OHf; q.OWf = p.OWf;
   q.out_stride = p.out_stride; q.out_off_y = p.out_off_y; q.out_off_x = p.out_off_x;
   q.Wt = g.Wt; q.Ht = g.Ht; q.Nt = g.Nt;
   q.tiles_h = p.OH / g.Ht;
   q.m_tiles = ceil_div(p.M, BM);
   // channel tile: whole N when small; otherwise split so that the persistent grid is filled
-  int bn = p.N <= 128 ? p.N : 128;
-  while (bn > 32 && bn % 32 == 0 && q.m_tiles * (p.N / bn) < sm_count() && p.N % (bn / 2) == 0) bn /= 2;
+  int bn = pick_bn(p.N);
+  while (bn <= 128 && bn > 32 && bn % 32 == 0 && q.m_tiles * (p.N / bn) < sm_count() && p.N % (bn / 2) == 0) bn /= 2;
   q.BN = bn;
   q.n_tiles = p.N / bn;
   q.rows_per_group = p.rows_per_group;

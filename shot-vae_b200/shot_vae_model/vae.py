@@ -163,14 +163,16 @@ class VariationalAutoEncoder(nn.Module):
                          in_ch=int(num_input_channels), temperature=float(sample_temperature))
         self._net = None
         self._ctx_pool = {}
-        self._pack_version = -1
+        self._pack_version = None
         self.device_noise = False      # True: draw eps/u on the device generator (benchmark mode)
         self.noise_source = None       # optional object with randn(*shape) / rand(*shape) (parity replays)
 
     # ---- reference checkpoints may carry nn.DataParallel's ".module." infix ---------------------
     def load_state_dict(self, state_dict, strict=True, **kw):
         cleaned = OrderedDict((k.replace(".module.", "."), v) for k, v in state_dict.items())
-        return super().load_state_dict(cleaned, strict=strict, **kw)
+        res = super().load_state_dict(cleaned, strict=strict, **kw)
+        self._pack_version = None           # the masters changed: repack before the next forward
+        return res
 
     # ---- arena binding ---------------------------------------------------------------------------
     def _bind(self):
@@ -185,15 +187,20 @@ class VariationalAutoEncoder(nn.Module):
             p.grad = None
         for k, b in bufs.items():
             b.data = net.b(k)
-        self._net, self._ctx_pool, self._pack_version = net, {}, -1
+        self._net, self._ctx_pool, self._pack_version = net, {}, None
         self.__dict__["_first_name"], self.__dict__["_first"] = next(iter(params.items()))
+        self.__dict__["_plist"] = list(params.values())
 
     def _ensure_bound(self):
         if self._net is None or self._first.data_ptr() != self._net.p(self._first_name).data_ptr():
             self._bind()
 
     def _pack_if_needed(self):
-        v = self._net.params._version
+        """Re-derive the bf16 operand copies of the conv / convT weights whenever the FP32 masters may have moved.
+        The Parameters are views of the arena with their OWN version counters (optimizer.step(), p.add_(),
+        load_state_dict() bump p._version, never the arena's), and the fused sv_sgd_step kernel bumps nothing, so
+        the signal is (sum of the parameters' versions, the net's explicit param_epoch that TrainStep advances)."""
+        v = (sum(p._version for p in self._plist), self._net.param_epoch)
         if v != self._pack_version:
             self._net.pack_weights()
             self._pack_version = v

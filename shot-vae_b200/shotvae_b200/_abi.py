@@ -96,6 +96,9 @@ _PROTOS = {
     "sv_mixup_lerp": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]),
     "sv_pairwise_kl_second_nearest": (C.c_int, [vp, vp, i32, i32, vp, vp, vp]),
     "sv_sgd_step": (C.c_int, [vp, vp, vp, vp, i64, vp]),
+    "sv_pairwise_dist": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
+    "sv_kl_pair_fwd_bwd": (C.c_int, [i32, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
+    "sv_augment_batch": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "sv_debug_halo_trace": (C.c_int, [vp]),
 }
 EXPORTS = sorted(_PROTOS)

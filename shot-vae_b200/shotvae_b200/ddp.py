@@ -7,27 +7,66 @@ block of every forward, each rank owns a replica and a batch shard, BatchNorm st
 replica (DataParallel's semantics), and the only exchange is one sum of the gradient arena per step
 (the SGD kernel divides by world_size).  Buckets follow the order in which the last backward
 finalises gradients: the decoder range (88 % of the bytes) first, then encoder + heads.
+
+Replicas start identical: construction broadcasts rank 0's parameters, BatchNorm buffers and momentum
+(nn.DataParallel gets that for free from its single master copy; torch DDP does the same broadcast).
+The per-rank noise streams must differ -- seed the CUDA generator per rank (bench.py does).
 """
 import torch
 import torch.distributed as dist
 
+DECODER_HEAD = "feature_reconstructor.decoder.0.weight"
+
 
 class GradReducer:
-    def __init__(self, net, group=None):
+    def __init__(self, net, group=None, broadcast=True):
+        """net: plan.Net (or any object with the same flat arenas: params / grads / momentum / running / nbt,
+        poff, n_params).  CPU arenas (gloo) are reduced synchronously -- that mode exists for the world_size-2
+        CPU tests of this class; the product path is CUDA + NCCL."""
         self.net, self.group = net, group
         self.world = dist.get_world_size(group)
-        self.stream = torch.cuda.Stream()
-        split = net.poff["feature_reconstructor.decoder.0.weight"][0]
+        self.cuda = net.grads.is_cuda
+        self.stream = torch.cuda.Stream(device=net.grads.device) if self.cuda else None
+        split = net.poff[DECODER_HEAD][0]
+        # the two-bucket split relies on the decoder owning the TAIL of the arena (state_dict order of the reference
+        # module tree: feature_extractor, heads, feature_reconstructor)
+        tail = [k for k, (o, _, _) in net.poff.items() if o >= split]
+        assert tail and all(k.startswith("feature_reconstructor.") for k in tail) and \
+            all(o >= split for k, (o, _, _) in net.poff.items() if k.startswith("feature_reconstructor.")), \
+            "decoder parameters are not the contiguous tail of the parameter arena"
         self.buckets = {"encoder": (0, split), "decoder": (split, net.n_params)}
         self.bytes_per_step = net.n_params * 4
+        if broadcast:
+            self.broadcast_state()
+
+    def broadcast_state(self, src=0):
+        """rank `src`'s parameters, BatchNorm running statistics / counters and momentum to every rank"""
+        for name in ("params", "running", "nbt", "momentum"):
+            t = getattr(self.net, name, None)
+            if t is not None and t.numel():
+                dist.broadcast(t, src=src, group=self.group)
+        if hasattr(self.net, "param_epoch"):
+            self.net.param_epoch += 1          # masters changed: bf16 operand copies must be re-derived
+
+    def state_checksum(self):
+        """debug aid: (max - min) over ranks of a parameter checksum; 0.0 when the replicas are identical"""
+        s = self.net.params.double().sum().reshape(1)
+        lo, hi = s.clone(), s.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        return float(hi - lo)
 
     def bucket_ready(self, name):
         """called on the compute stream right after the last kernel that writes this gradient range"""
         s, e = self.buckets[name]
+        if not self.cuda:
+            dist.all_reduce(self.net.grads[s:e], op=dist.ReduceOp.SUM, group=self.group)
+            return
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             dist.all_reduce(self.net.grads[s:e], op=dist.ReduceOp.SUM, group=self.group)
 
     def wait_all(self):
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)

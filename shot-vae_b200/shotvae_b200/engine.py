@@ -91,7 +91,8 @@ class TrainStep:
         self.graph = None
         self.launches_per_step = None
         self._epoch = None
-        self._steps_done = 0
+        self._steps_done = 0         # optimizer steps taken (momentum first-step rule; restored by load_state_dict)
+        self._calls = 0              # run_resident() calls on THIS object (eager warm-up, then graph capture)
         # pinned host staging for the end-to-end path
         pin = lambda *s, dtype=f32: torch.zeros(*s, dtype=dtype).pin_memory()
         self.h_img_l, self.h_img_u = pin(B, net.in_ch, 32, 32), pin(B, net.in_ch, 32, 32)
@@ -139,19 +140,23 @@ class TrainStep:
         idx_u = torch.arange(B) if self.h["om"] else torch.randperm(B)
         return lam_l, idx_l, lam_u, idx_u
 
-    def stage_draws(self, draws, label_l_host):
+    def stage_draws(self, draws, label_l):
+        """label_l: the labelled batch's labels, host (pinned staging) or device"""
         if draws is None:
             return
         lam_l, idx_l, lam_u, idx_u = draws
         self.h_lam.copy_(torch.tensor([lam_l, 1 - lam_l, lam_u, 1 - lam_u], dtype=torch.float64).float())
         self.h_idx[0].copy_(idx_l)
         self.h_idx[1].copy_(idx_u)
-        self.h_idx[2].copy_(label_l_host[idx_l])
         self.lam.copy_(self.h_lam, non_blocking=True)
         self.idx_l.copy_(self.h_idx[0], non_blocking=True)
         if not self.h["om"]:
             self.idx_u.copy_(self.h_idx[1], non_blocking=True)
-        self.s_lab.copy_(self.h_idx[2], non_blocking=True)
+        if label_l.is_cuda:
+            torch.index_select(label_l, 0, self.idx_l, out=self.s_lab)     # smoothed_disc_label = disc_label[index] (mixup.py:37)
+        else:
+            self.h_idx[2].copy_(label_l[idx_l])
+            self.s_lab.copy_(self.h_idx[2], non_blocking=True)
 
     # ---- the launch sequence -----------------------------------------------------------------------
     def _losses_first(self, ctx, rec):
@@ -321,7 +326,7 @@ class TrainStep:
             self.sgd_hyper[4:5].zero_()       # momentum buffer is initialised; torch semantics from now on
         if not self.use_graph:
             self._run_parts_eager()
-        elif self.graph is None and self._steps_done >= 2:
+        elif self.graph is None and self._calls >= 2:
             n0 = _abi.launch_count()
             groups = [(0, 1, 2)] if self.reducer is None else [(0,), (1,), (2,)]
             graphs = []
@@ -340,6 +345,8 @@ class TrainStep:
             self._run_parts_eager()           # eager warm-up steps allocate every buffer
             self.launches_per_step = _abi.launch_count() - n0
         self._steps_done += 1
+        self._calls += 1
+        self.net.param_epoch += 1             # the fused SGD moved the FP32 masters: the drop-in forward must repack
 
     def _replay(self):
         if self.reducer is None:
@@ -354,20 +361,26 @@ class TrainStep:
 
     def load_inputs(self, image_l, label_l, image_u, label_u, draws="auto"):
         """host -> device copy of one (labelled, unlabelled) batch pair through pinned staging buffers,
-        plus the host RNG draws of this step"""
+        plus the host RNG draws of this step.  Batches that already live on the device (lib.dataloader.DeviceLoader)
+        are copied device to device and never touch the host."""
         # images that already sit in pinned host memory are copied straight from there (the caller must leave them
         # untouched until the step has been synchronised -- step() does that before it returns); anything else goes
         # through the pinned staging buffers
         for dst, staged, src in ((self.img_l, self.h_img_l, image_l), (self.img_u, self.h_img_u, image_u)):
-            if src.device.type == "cpu" and src.is_pinned() and src.dtype == dst.dtype and src.shape == dst.shape and src.is_contiguous():
+            if src.is_cuda:
+                dst.copy_(src)
+            elif src.is_pinned() and src.dtype == dst.dtype and src.shape == dst.shape and src.is_contiguous():
                 dst.copy_(src, non_blocking=True)
             else:
                 staged.copy_(src)
                 dst.copy_(staged, non_blocking=True)
-        self.h_label_l.copy_(label_l); self.h_label_u.copy_(label_u)
-        self.label_l.copy_(self.h_label_l, non_blocking=True)
-        self.label_u.copy_(self.h_label_u, non_blocking=True)
-        self.stage_draws(self.draw_host() if draws == "auto" else draws, self.h_label_l)
+        for dst, staged, src in ((self.label_l, self.h_label_l, label_l), (self.label_u, self.h_label_u, label_u)):
+            if src.is_cuda:
+                dst.copy_(src)
+            else:
+                staged.copy_(src)
+                dst.copy_(staged, non_blocking=True)
+        self.stage_draws(self.draw_host() if draws == "auto" else draws, self.label_l if label_l.is_cuda else self.h_label_l)
 
     def h2d_bytes(self):
         n = self.h_img_l.numel() * 4 * 2 + self.B * 8 * 2
@@ -389,6 +402,45 @@ class TrainStep:
         for sfx in ("l", "u"):
             t["prior_" + sfx] = s["kbc"] * abs(t["klc_" + sfx] - s["cmi"]) + s["kbd"] * abs(t["kld_" + sfx] - s["dmi"])
         return t
+
+    # ---- optimizer state (reference checkpoint field 'optimizer', main_shot_vae.py:209,241) ------------------
+    def state_dict(self):
+        """The fused optimizer's state in torch.optim.SGD's state_dict layout (parameters numbered in
+        model.parameters() order, one 'momentum_buffer' each), so the reference's checkpoint dict
+        {'epoch', 'args', 'state_dict', 'optimizer'} can carry it and torch.optim.SGD.load_state_dict accepts it."""
+        net, h = self.net, self.h
+        n = len(net.pnames)
+        state = {}
+        if self._steps_done > 0:
+            for i, k in enumerate(net.pnames):
+                o, cnt, shp = net.poff[k]
+                state[i] = {"momentum_buffer": net.momentum[o:o + cnt].view(shp).clone()}
+        group = dict(lr=self._lr, momentum=h["momentum"], dampening=0, weight_decay=h["wd"], nesterov=False, maximize=False,
+                     foreach=None, differentiable=False, fused=None, params=list(range(n)))
+        return {"state": state, "param_groups": [group], "shotvae": {"steps_done": self._steps_done}}
+
+    def load_state_dict(self, sd):
+        """accepts state_dict() above or a plain torch.optim.SGD state dict (a reference checkpoint's 'optimizer')"""
+        net = self.net
+        groups = sd["param_groups"]
+        assert len(groups) == 1 and len(groups[0]["params"]) == len(net.pnames), "optimizer state does not match the model"
+        state = sd.get("state", {})
+        net.momentum.zero_()
+        have = 0
+        for i, k in enumerate(net.pnames):
+            ent = state.get(i, state.get(str(i)))
+            buf = None if ent is None else ent.get("momentum_buffer")
+            if buf is not None:
+                o, cnt, shp = net.poff[k]
+                net.momentum[o:o + cnt].view(shp).copy_(buf.to(net.device, torch.float32))
+                have += 1
+        assert have in (0, len(net.pnames)), "partial momentum state (%d of %d buffers)" % (have, len(net.pnames))
+        # torch semantics: a parameter without a momentum buffer takes buf = grad on its next step
+        self._steps_done = int(sd.get("shotvae", {}).get("steps_done", 1 if have else 0))
+        if have == 0:
+            self._steps_done = 0
+        self.h["momentum"], self.h["wd"] = float(groups[0]["momentum"]), float(groups[0]["weight_decay"])
+        self.set_lr(float(groups[0]["lr"]))
 
     def set_noise(self, eps4, unif2):
         """parity mode: host-drawn noise in pass order (P1, P2, P3, P4) / (P3, P4)"""

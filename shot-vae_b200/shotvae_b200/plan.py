@@ -212,6 +212,7 @@ class Net:
         for k, v in named_buffers.items():
             self.b(k).copy_(v.detach().to(self.device))
         self.wg_ws = torch.empty(WG_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
+        self.param_epoch = 0      # advanced by whoever rewrites the FP32 masters behind torch's back (TrainStep's fused SGD)
         self.dry = False          # dry mode: build buffers / records only, launch nothing (Ctx views -> parent tape)
         self.eval_bn = False      # True: BatchNorm normalises with the running statistics (model.eval(), reference valid()/test())
         self.side = None          # optional torch.cuda.Stream for the weight gradients (set by the engine)

@@ -78,7 +78,8 @@ IMPLS = [1, 2, 3]   # 1 = mma.sync, 2 = tcgen05 + per-tap TMA, 3 = tcgen05 halo-
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("cin,cout,H,stride,k,NB", [
     (32, 32, 32, 1, 3, 4), (16, 32, 32, 1, 3, 3), (32, 64, 32, 2, 3, 4), (64, 64, 16, 1, 3, 8), (64, 128, 16, 2, 3, 8),
-    (128, 128, 8, 1, 3, 16), (16, 32, 32, 1, 1, 2), (32, 64, 32, 2, 1, 4), (160, 160, 8, 1, 3, 2), (16, 16, 32, 1, 3, 5)])
+    (128, 128, 8, 1, 3, 16), (16, 32, 32, 1, 1, 2), (32, 64, 32, 2, 1, 4), (160, 160, 8, 1, 3, 2), (16, 16, 32, 1, 3, 5),
+    (160, 160, 32, 1, 3, 2), (320, 320, 16, 1, 3, 4), (640, 640, 8, 1, 3, 4), (16, 160, 32, 1, 3, 2), (160, 320, 16, 1, 1, 4)])
 def test_conv_fprop_matches_torch(sv, impl, cin, cout, H, stride, k, NB):
     from shotvae_b200.plan import conv_taps
     torch.manual_seed(cin * 1000 + cout + H + stride)
@@ -118,6 +119,63 @@ def test_convT_fprop_phases_match_torch(sv, impl, cin, cout, Hin, NB):
               n_valid=cout, impl=impl)
     assert rel_rms(from_nhwc(out)[:, :cout], want) < 4e-3
     assert rel_rms(from_nhwc(outf), want) < 1e-3
+
+
+# ---- the benchmark regime: NB = 256 images per forward launch ([P1|P3] / [P2|P4], two pass groups) and NB = 512 per
+# backward launch (four pass groups), every stride-1 conv shape of WRN-28-2.  Each persistent CTA then runs
+# 8 ... 31 tiles, so the TMEM accumulator ring (8 deep), the shared-memory stage ring and the cross-tile BatchNorm
+# statistics registers all wrap -- teacher-forced against torch FP32 on the same bf16-rounded operands.
+WRN282_SHAPES = [(16, 32, 32, 3), (32, 32, 32, 3), (16, 32, 32, 1), (64, 64, 16, 3), (128, 128, 8, 3)]
+
+
+@pytest.mark.parametrize("NB,G", [(256, 2), (512, 4)])
+@pytest.mark.parametrize("cin,cout,H,k", WRN282_SHAPES)
+def test_conv_fprop_benchmark_batch_matches_torch(sv, cin, cout, H, k, NB, G):
+    from shotvae_b200.plan import conv_taps
+    from shotvae_b200._abi import lib, IgemmArgs
+    torch.manual_seed(cin * 100 + cout + H + NB)
+    x, w = bf(torch.randn(NB, cin, H, H)), bf(torch.randn(cout, cin, k, k) * 0.1)
+    resid = bf(torch.randn(NB, cout, H, H))
+    torch.set_num_threads(max(1, (os.cpu_count() or 8)))
+    want = F.conv2d(x, w, None, 1, k // 2) + resid
+    taps = conv_taps(k, k // 2)
+    # the kernel the engine picks for this shape (halo-tile layout when it covers it, else auto selection)
+    probe = IgemmArgs()
+    probe.A = probe.Wt = probe.out_bf16 = 4096          # (alignment checks only; never dereferenced)
+    probe.NB, probe.H, probe.W, probe.C, probe.OH, probe.OW, probe.N, probe.T = NB, H, H, cin, H, H, cout, len(taps)
+    probe.in_stride, probe.out_stride, probe.OHf, probe.OWf, probe.group_images, probe.w_layout = 1, 1, H, H, NB // G, 1
+    from shotvae_b200._abi import taps_array
+    probe.dy, probe.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
+    impl = 3 if lib.sv_igemm_fprop_supports(C.byref(probe), 3) and not (cin >= 128 and cout >= 128) else 0
+    Wt = pack(sv, w, cout, cin, taps, cout, cin, cin * k * k, k * k, 1, impl)
+    out = torch.empty(NB, H, H, cout, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(G, 2, cout, device="cuda")
+    igemm(sv, nhwc(x), Wt, taps, NB, H, H, cin, H, H, cout, out=out, res=nhwc(resid), stats=stats, group_images=NB // G, impl=impl)
+    got = from_nhwc(out)
+    assert rel_rms(got, want) < 4e-3
+    gq = got.view(G, NB // G, cout, -1)
+    assert rel_rms(stats[:, 0].cpu(), gq.sum(dim=(1, 3))) < 2e-3
+    assert rel_rms(stats[:, 1].cpu(), (gq * gq).sum(dim=(1, 3))) < 1e-3
+    # second launch into the same buffers: the rings must come back to the same state (bit-identical output)
+    out2 = torch.empty_like(out)
+    igemm(sv, nhwc(x), Wt, taps, NB, H, H, cin, H, H, cout, out=out2, res=nhwc(resid), impl=impl)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("cin,cout,H,k", WRN282_SHAPES)
+def test_conv_wgrad_benchmark_batch_matches_autograd(sv, cin, cout, H, k):
+    from shotvae_b200.plan import conv_taps
+    NB = 512
+    torch.manual_seed(17 + cin + cout + H)
+    x = bf(torch.randn(NB, cin, H, H))
+    w = torch.randn(cout, cin, k, k, requires_grad=True)
+    g = bf(torch.randn(NB, cout, H, H) * 0.1)
+    torch.set_num_threads(max(1, (os.cpu_count() or 8)))
+    F.conv2d(x, w, None, 1, k // 2).backward(g)
+    grad = torch.zeros(cout, cin, k, k, device="cuda")
+    wgrad(sv, nhwc(x), nhwc(g).view(-1, cout), conv_taps(k, k // 2), NB, H, H, cin, H, H, cout, 1, grad, cout, cin,
+          cin * k * k, k * k, 1, 1, 2)
+    assert rel_rms(grad.cpu(), w.grad) < 2e-3
 
 
 @pytest.mark.parametrize("impl", [0, 2])

@@ -1,0 +1,166 @@
+"""GPU parity at the configuration bench.py times: batch 128 labelled + 128 unlabelled per pass group, i.e.
+NB = 256 images per forward launch and NB = 512 per backward launch -- every persistent CTA of the tcgen05
+kernels processes many tiles, so the TMEM accumulator ring, the shared-memory stage ring and the cross-tile
+BatchNorm statistics all wrap (main_shot_vae.py:38,280-366).
+
+* C2 (WRN-28-2, nd=10, --br) against the committed golden of the UNMODIFIED reference's train()
+  (tests/golden/c2_wrn28x2_nd10_b128_e0.json): the oracle is re-run with the golden's seeds (and re-checked against
+  the golden), its recorded host draws are fed to the fused engine / the drop-in modules.
+* C3 (nd=100, --br) and C5 (M2 step, PreActResNet18, nd=100) at B = 128 against the oracle.
+
+Tolerances: ELBO terms 1e-3 relative (north star); the small categorical KL absolute; parameter updates as relative
+L2 per group against the FP32 oracle next to the same-precision control documented in tests/test_gpu_step.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_gpu_step import _feed, _oracle_step_with_sgd, _report, build_model, grad_errors, rel, run_case
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD_B128 = os.path.join(HERE, "golden", "c2_wrn28x2_nd10_b128_e0.json")
+
+
+def _check_terms(got, want, m2, tag):
+    rep = {k: dict(got=got[k], want=want[k]) for k in want if k in got and isinstance(want[k], float)}
+    _report("terms_" + tag, rep)
+    for k in ("rec_l", "klc_l", "rec_u", "klc_u"):
+        assert abs(got[k] - want[k]) < 1e-3 * abs(want[k]), (k, got[k], want[k])
+    for k in ("kld_l", "kld_u"):
+        assert abs(got[k] - want[k]) < 1e-3 * max(1.0, abs(want["klc_l"])), (k, got[k], want[k])
+    assert abs(got["kl_inference"] - want["kl_inference"]) < 5e-3 * abs(want["kl_inference"])
+    assert abs(got["disc_post_l"] - want["disc_post_l"]) < 5e-3 * abs(want["disc_post_l"])
+    if not m2:
+        assert abs(got["disc_post_u"] - want["disc_post_u"]) < 5e-3 * abs(want["disc_post_u"])
+        assert abs(got["cont_post_u"] - want["cont_post_u"]) < 5e-2 * abs(want["cont_post_u"])
+        # lambda_l ~ Beta(0.1, 0.1) is ~0 or ~1, so ||mu_2 - mu_smoothed||^2 is a difference of two nearly identical
+        # forwards: ~1e-10 in FP32, bf16 noise here -- gated absolutely on the scale of the continuous KL it is added to
+        assert abs(got["cont_post_l"] - want["cont_post_l"]) < 2e-3 * max(1.0, abs(want["klc_l"])), (got["cont_post_l"], want["cont_post_l"])
+
+
+def _check_state(model, st, ost, m2, tag):
+    from oracle import shotvae_oracle as O
+    sd = model.state_dict()
+    upd = {k: sd[k].float().cpu() - st[k].float() for k in O.param_names(ost)}
+    wupd = {k: ost[k].detach().float() - st[k].float() for k in O.param_names(ost)}
+    errs = grad_errors(upd, wupd)
+    _report("update_rel_l2_" + tag, errs)
+    assert errs["decoder"] < 0.15 and errs["heads"] < 0.15 and errs["encoder"] < 0.65, errs
+    rs = max(rel(sd[k], ost[k]) for k in ost if k.endswith("running_mean") or k.endswith("running_var"))
+    _report("running_stats_" + tag, rs)
+    assert rs < 3e-2
+    nb = 2 if m2 else 4
+    assert all(int(sd[k]) == nb for k in ost if k.endswith("num_batches_tracked") and "feature_extractor" in k)
+    return sd
+
+
+def test_engine_c2_b128_matches_reference_golden():
+    """TrainStep at the benchmark batch, teacher-fed with the draws of the reference golden; step 1 eager, then a
+    second engine replays steps 1-3 of the same trajectory with the third one through the captured CUDA graph."""
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    from tests.golden.make_golden import sample_positions
+    g = json.load(open(GOLD_B128))
+    c = g["case"]
+    assert (c["net"], c["nd"], c["batch"], c["om"], c["m2"]) == ("wideresnet-28-2", 10, 128, False, False)
+    hyper = O.default_hyper("Cifar10")
+    hyper["br"] = c.get("br", True)
+    st, ost, (il, ll, iu, lu), outs, logs = _oracle_step_with_sgd(c["net"], c["nd"], c["batch"], c["epoch"], hyper, c["rng_seed"],
+                                                                  c["data_seed"], nsteps=3)
+    want = outs[0]
+    # the oracle run IS the golden case: same draws, same terms as the unmodified reference recorded
+    assert [k for k, _ in logs[0]] == g["draw_kinds"]
+    assert [v for k, v in logs[0] if k == "beta"] == g["betas"]
+    for a, b in zip((want["rec_l"], want["klc_l"], want["kld_l"], want["rec_u"], want["klc_u"], want["kld_u"]), g["elbo_terms"][0] + g["elbo_terms"][1]):
+        assert abs(a - b) <= 1e-5 * abs(b) + 1e-7
+    hy = {k: v for k, v in hyper.items() if k != "temperature"}
+    # ---- (1) one eager step from the golden's initial state
+    model = build_model(c["net"], c["nd"], st).train()
+    ts = TrainStep(model, c["batch"], hyper=hy, use_graph=False, device_noise=False)
+    ts.set_epoch(c["epoch"])
+    got = ts.step(il, ll, iu, lu, draws=_feed(ts, logs[0], False))
+    _check_terms(got, want, False, "engine_c2_b128_golden")
+    for k, ref in zip(("rec_l", "klc_l", "kld_l"), g["elbo_terms"][0]):      # and directly against the reference's numbers
+        assert abs(got[k] - ref) < 1e-3 * max(abs(ref), 1.0 if k == "kld_l" else 0.0), (k, got[k], ref)
+    assert abs(got["kl_inference"] - g["kl_inference"]) < 5e-3 * abs(g["kl_inference"])
+    # P1 / P3 outputs of the engine's pass buffers against the golden's fixed-position samples of the reference tensors
+    A = ts.ctxA
+    B = c["batch"]
+    for gi, (pi, names) in enumerate(((0, ("mu", "ls", "la")), (2, ("mu", "ls", "la")))):
+        for n, gs in zip(names, g["model_outputs"][pi][1:4]):
+            t = A.bufs[n][gi * B:(gi + 1) * B].float().cpu().double().flatten()
+            assert t.numel() == gs["numel"]
+            assert abs(float(t.norm()) - gs["l2"]) < 2e-2 * gs["l2"], (n, float(t.norm()), gs["l2"])
+            scale = gs["l2"] / gs["numel"] ** 0.5
+            for p, v in zip(sample_positions(t.numel()), gs["samples"]):
+                assert abs(float(t[p]) - v) < 0.1 * scale + 2e-2 * abs(v), (n, p, float(t[p]), v)
+    # post-step state: against the oracle's full tensors, and (norm pin) against the golden's summaries
+    O1 = _oracle_step_with_sgd(c["net"], c["nd"], c["batch"], c["epoch"], hyper, c["rng_seed"], c["data_seed"], nsteps=1)[1]
+    sd = _check_state(model, st, O1, False, "engine_c2_b128_golden")
+    for k, gs in g["post_state"].items():
+        if gs["numel"] > 1:
+            assert abs(float(sd[k].double().norm()) - gs["l2"]) < 5e-3 * gs["l2"] + 1e-6, (k, float(sd[k].double().norm()), gs["l2"])
+    # ---- (2) the captured graph at B = 128: steps 1-3 of the same trajectory, the third is a graph replay
+    model2 = build_model(c["net"], c["nd"], st).train()
+    tg = TrainStep(model2, c["batch"], hyper=hy, use_graph=True, device_noise=False)
+    tg.set_epoch(c["epoch"])
+    for i in range(3):
+        got_i = tg.step(il, ll, iu, lu, draws=_feed(tg, logs[i], False))
+        for k in ("rec_l", "klc_l", "rec_u", "klc_u"):
+            tol = 1e-3 if i == 0 else 5e-3      # later steps inherit the bf16 trajectory difference
+            assert abs(got_i[k] - outs[i][k]) < tol * abs(outs[i][k]), (i, k, got_i[k], outs[i][k])
+    assert tg.graph is not None and tg.launches_per_step > 150
+    errs = grad_errors({k: v.float().cpu() for k, v in model2.state_dict().items() if k in O.param_names(ost)},
+                       {k: ost[k].detach().float() for k in O.param_names(ost)})
+    _report("state_after_3_steps_rel_l2_engine_c2_b128_graph", errs)
+    assert errs["all"] < 2e-2, errs
+
+
+def test_dropin_c2_b128_matches_reference_golden():
+    """the drop-in modules (autograd path, what the unmodified main_shot_vae.train drives) at B = 128"""
+    g = json.load(open(GOLD_B128))
+    c = g["case"]
+    want, got, grads, wgrads, model, ost, ctx = run_case(c["net"], c["nd"], c["batch"], c["epoch"], c["om"], c.get("br", True),
+                                                         data_seed=c["data_seed"], rng_seed=c["rng_seed"])
+    for k, ref in zip(("rec_l", "klc_l", "kld_l", "rec_u", "klc_u", "kld_u"), g["elbo_terms"][0] + g["elbo_terms"][1]):
+        assert abs(want[k] - ref) <= 1e-5 * abs(ref) + 1e-7                       # oracle == reference golden
+        assert abs(got[k] - ref) < 1e-3 * max(abs(ref), 1.0 if k.startswith("kld") else 0.0), (k, got[k], ref)
+    for k in ("disc_post_l", "disc_post_u"):
+        assert abs(got[k] - want[k]) < 5e-3 * abs(want[k]), (k, got[k], want[k])
+    assert abs(got["cont_post_l"] - want["cont_post_l"]) < 2e-3 * max(1.0, abs(want["klc_l"]))
+    assert abs(got["cont_post_u"] - want["cont_post_u"]) < 5e-2 * abs(want["cont_post_u"])
+    errs = grad_errors(grads, wgrads)
+    _report("grad_rel_l2_dropin_c2_b128_golden", errs)
+    assert errs["decoder"] < 0.15 and errs["heads"] < 0.15 and errs["encoder"] < 0.65, errs
+    # gradient norms against the reference's recorded norms, per parameter group
+    for grp in ("decoder", "heads"):
+        num = sum(float(p.double().norm()) ** 2 for k, p in grads.items() if _grp(k) == grp) ** 0.5
+        den = sum(gs["l2"] ** 2 for k, gs in g["grads"].items() if _grp(k) == grp) ** 0.5
+        assert abs(num - den) < 5e-2 * den, (grp, num, den)
+
+
+def _grp(name):
+    return "encoder" if name.startswith("feature_extractor") else ("decoder" if name.startswith("feature_reconstructor") else "heads")
+
+
+@pytest.mark.parametrize("net,nd,epoch,m2,dataset,br", [
+    ("wideresnet-28-2", 100, 100, False, "Cifar100", True),      # C3: Cifar100-shaped, --br
+    ("preactresnet18", 100, 100, True, "Cifar100", False),       # C5: M2 step, PreActResNet18
+])
+def test_engine_c3_c5_b128_match_oracle(net, nd, epoch, m2, dataset, br):
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    B = 128
+    hyper = O.default_hyper(dataset, m2)
+    hyper["br"] = br
+    st, ost, (il, ll, iu, lu), outs, logs = _oracle_step_with_sgd(net, nd, B, epoch, hyper, 5, 11, m2)
+    model = build_model(net, nd, st).train()
+    ts = TrainStep(model, B, hyper={k: v for k, v in hyper.items() if k != "temperature"}, m2=m2, use_graph=False, device_noise=False)
+    ts.set_epoch(epoch)
+    got = ts.step(il, ll, iu, lu, draws=_feed(ts, logs[0], m2))
+    tag = "engine_%s_nd%d_b128_e%d%s%s" % (net, nd, epoch, "_m2" if m2 else "", "_br" if br else "_mse")
+    _check_terms(got, outs[0], m2, tag)
+    _check_state(model, st, ost, m2, tag)
