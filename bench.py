@@ -10,9 +10,13 @@ Prints ONE JSON line (rank 0).  `value` is images/s with the inputs already resi
 `TrainStep.step(host tensors)`: pinned-host -> device copies of the batch + the host RNG draws, the
 step, and a device -> host read of the loss terms, every step.  `roofline` describes the dominant
 kernel family (the implicit-GEMM convolution kernel), timed with CUDA events around each launch in
-an instrumented eager replay of the same launch sequence.  `cpu_baseline` is the CPU oracle port
-(oracle/shotvae_oracle.py, torch FP32 ATen kernels = what the reference executes on a CPU) timed
-on this box's host cores on a bounded sample.  `--impl reference` times that CPU path alone.
+an instrumented eager replay of the same launch sequence.  `cpu_baseline` / `--impl reference` time the UNMODIFIED
+reference's own `train()` (baseline/_ref, driven by baseline/ref_harness.py in a subprocess: FP32 ATen kernels on this
+box's host cores, all of them) on a bounded sample of the same workload; when baseline/_ref is absent they fall back to
+the CPU oracle port (kind "port").  `gpu_reference` is the same unmodified reference on ONE GPU through torch's eager
+CUDA path (cuDNN TF32) -- the kernel-library baseline the hand-written kernels are measured against.
+`python bench.py --kernels` times the bandwidth-bound kernels (ELBO loss+gradient, mixup, SGD, augmentation) at
+B = 16 384 (HBM-resident) and at B = 128 (launch floor) and prints their achieved GB/s against the measured HBM peak.
 """
 import argparse
 import json
@@ -46,9 +50,9 @@ EPOCH = 100        # schedules evaluated at a fixed epoch where every loss term 
 BATCH = 128
 
 
-# DRAM bytes per launch of the sv_igemm_fprop family (C2, N=1), from the ncu pass summarised in
-# profiles/r01_launches_n1_summary.md: 14.02 MB against 19.7 MB algorithmic (outputs and re-read inputs stay in L2)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 14.02e6
+# roofline.traffic (DRAM bytes per launch) needs ncu and is therefore not measured inside this run: the bench line carries
+# null and names the launch-list summary generated with ncu from the same commit
+TRAFFIC_SOURCE = "profiles/r02_launches_n1_summary.md"
 
 
 def peaks():
@@ -97,10 +101,39 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_arm(cfg, steps, warmup, threads=None):
-    """the reference's CPU path (oracle port: same ATen FP32 ops the reference issues) on the host cores"""
+def run_ref_harness(config, device, steps, warmup, gpu_index="0", timeout=1500):
+    """the UNMODIFIED reference's own train() (baseline/_ref) in a subprocess -> the harness's JSON dict, or None"""
+    harness = os.path.join(ROOT, "baseline", "ref_harness.py")
+    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "main_shot_vae.py")):
+        return None
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "CUDA_VISIBLE_DEVICES"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, harness, "--device", device, "--config", config, "--steps", str(steps), "--warmup", str(warmup),
+                            "--batch", str(BATCH), "--epoch", str(EPOCH), "--gpu-index", str(gpu_index)], capture_output=True, text=True,
+                           timeout=timeout, env=env)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        out = json.loads(lines[-1]) if lines else None
+        if out is None or "unavailable" in out:
+            print("[bench] reference harness: %s" % (r.stderr[-500:] if out is None else out), file=sys.stderr)
+            return None
+        return out
+    except Exception as e:
+        print("[bench] reference harness failed: %r" % (e,), file=sys.stderr)
+        return None
+
+
+def cpu_reference_arm(config, cfg, steps, warmup):
+    """The reference's CPU implementation of the step on the host cores: its own train() through the harness (kind
+    "reference"), or -- only when baseline/_ref is absent -- the CPU oracle port (same ATen FP32 ops)."""
+    h = run_ref_harness(config, "cpu", steps, warmup)
+    if h is not None:
+        return dict(value=h["images_per_s"], unit="images/s", cores=h["cores"], kind="reference", ms_per_step=h["ms_per_step"],
+                    sample="%d optimizer steps (batch 128 labelled + 128 unlabelled, FP32) of the unmodified reference's %s on list loaders "
+                           "after %d warm-up steps, %.1f s, torch %s CPU" % (steps, h["entry"], warmup, h["seconds"], h["torch"]))
     from oracle import shotvae_oracle as O
-    threads = threads or os.cpu_count()
+    threads = os.cpu_count()
     torch.set_num_threads(threads)
     hyper = O.default_hyper(cfg["dataset"], cfg["m2"])
     hyper["br"] = cfg["br"]
@@ -120,6 +153,78 @@ def cpu_reference_arm(cfg, steps, warmup, threads=None):
     return dict(value=BATCH * steps / tot, unit="images/s", cores=threads, kind="port",
                 sample="%d full training steps (batch 128+128, FP32) of the CPU oracle after %d warm-up, %.1f s" % (steps, warmup, tot),
                 ms_per_step=1e3 * tot / steps)
+
+
+def bandwidth_kernels_leg():
+    """`--kernels`: the bandwidth-bound kernels of the step alone, CUDA events over back-to-back launches on rotating
+    buffers.  B = 16 384 streams far more than the 126 MB L2 (the HBM roofline); B = 128 is the size the step runs them at
+    (time against the launch floor)."""
+    from shotvae_b200 import _abi
+    from shotvae_b200._abi import lib, check, ptr
+    pk, how = peaks()
+    peak = pk["hbm_gbs"]
+    dev = torch.device("cuda")
+    st = _abi.stream()
+    out = {}
+
+    def timed(name, B, nbytes, make, launch, reps=30, nbuf=4):
+        bufs = [make() for _ in range(nbuf)]
+        for b in bufs:
+            launch(b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            launch(bufs[i % nbuf])
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / reps
+        out.setdefault(name, {})["B=%d" % B] = dict(us=us, algorithmic_mb=nbytes / 1e6, gbps=nbytes / (us * 1e-6) / 1e9,
+                                                    frac_of_hbm_peak=nbytes / (us * 1e-6) / 1e9 / peak)
+
+    D, nd, ch, hw = 128, 10, 3, 1024
+    for B in (16384, 128):
+        n_img = B * ch * hw
+        coef = torch.tensor([1e-3] * 16, device=dev)
+        # ELBO reconstruction term + gradient: read x, x_hat (fp32), write d x_hat (bf16 NHWC padded to 16 channels, the layout the
+        # decoder backward consumes) -- SURVEY 8(d): 3 * B * 3072 * 4 bytes with an fp32 gradient; here the gradient is 16 ch bf16
+        def mk_rec():
+            return dict(x=torch.rand(B, ch, 32, 32, device=dev), xh=torch.randn(B, 32, 32, ch, device=dev), t=torch.zeros(4, device=dev),
+                        g=torch.empty(B, 32, 32, 16, dtype=torch.bfloat16, device=dev))
+        timed("sv_elbo_rec_fwd_bwd", B, n_img * 4 * 2 + B * hw * 16 * 2, mk_rec,
+              lambda b: check(lib.sv_elbo_rec_fwd_bwd(ptr(b["x"]), ptr(b["xh"]), 1, B, ch, hw, 1, 1.0, ptr(coef), ptr(b["t"]), ptr(b["g"]), 16, None, st)))
+        def mk_recf():
+            return dict(x=torch.rand(B, ch, 32, 32, device=dev), xh=torch.randn(B, ch, 32, 32, device=dev), t=torch.zeros(4, device=dev),
+                        g=torch.empty(B, ch, 32, 32, device=dev))
+        timed("sv_elbo_rec_fwd_bwd (fp32 NCHW gradient, the drop-in criterion)", B, n_img * 4 * 3, mk_recf,
+              lambda b: check(lib.sv_elbo_rec_fwd_bwd(ptr(b["x"]), ptr(b["xh"]), 0, B, ch, hw, 1, 1.0, None, ptr(b["t"]), None, 0, ptr(b["g"]), st)))
+        # mixup / label smoothing: read image + gathered partner, write the mixed image (fp32) + small latents
+        def mk_mix():
+            return dict(x=torch.rand(B, ch, 32, 32, device=dev), mu=torch.randn(B, D, device=dev), ls=torch.randn(B, D, device=dev) * 0.1,
+                        la=torch.log_softmax(torch.randn(B, nd, device=dev), 1), idx=torch.randperm(B, device=dev), lam=torch.tensor([0.3, 0.7], device=dev),
+                        o=torch.empty(B, ch, 32, 32, device=dev), omu=torch.empty(B, D, device=dev), osg=torch.empty(B, D, device=dev),
+                        oal=torch.empty(B, nd, device=dev))
+        timed("sv_mixup_lerp", B, n_img * 4 * 3 + B * (2 * D + nd) * 4 * 3, mk_mix,
+              lambda b: check(lib.sv_mixup_lerp(ptr(b["x"]), ptr(b["mu"]), ptr(b["ls"]), ptr(b["la"]), ptr(b["idx"]), ptr(b["lam"]), B, ch, hw, D, nd,
+                                                ptr(b["o"]), None, 0, ptr(b["omu"]), ptr(b["osg"]), ptr(b["oal"]), st)))
+        # device augmentation: read uint8 images, write fp32 NCHW
+        def mk_aug():
+            return dict(d=torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8, device=dev), idx=torch.randperm(B, device=dev),
+                        p=torch.cat([torch.randint(0, 9, (B, 2), device=dev), torch.randint(0, 2, (B, 1), device=dev)], 1).to(torch.int32),
+                        o=torch.empty(B, ch, 32, 32, device=dev))
+        timed("sv_augment_batch", B, n_img * (1 + 4), mk_aug,
+              lambda b: check(lib.sv_augment_batch(ptr(b["d"]), ptr(b["idx"]), ptr(b["p"]), B, 3, 32, 32, 4, 32, 32, 1, ptr(b["o"]), st)))
+    # SGD over the flat arena: read p, g, m; write p, m, g (zeroed)
+    for n, tag in ((12790346, "C2 arena (12.79 M parameters)"), (47933770, "C4 arena (47.93 M parameters)")):
+        na = (n + 3) // 4 * 4
+        hyper = torch.tensor([0.1, 0.9, 5e-4, 1.0, 0.0, 0, 0, 0], device=dev)
+        def mk_sgd():
+            return dict(p=torch.randn(na, device=dev), g=torch.randn(na, device=dev), m=torch.randn(na, device=dev))
+        timed("sv_sgd_step " + tag, n, n * 4 * 6, mk_sgd, lambda b: check(lib.sv_sgd_step(ptr(b["p"]), ptr(b["g"]), ptr(b["m"]), ptr(hyper), n, st)),
+              nbuf=3)
+    return dict(impl="ours", leg="bandwidth kernels", unit="GB/s", hbm_peak_gbs=peak, peak_source=how, kernels=out,
+                note="algorithmic bytes / CUDA-event time over 30 back-to-back launches on rotating buffers; B = 16384 operands exceed the L2, "
+                     "B = 128 is the in-step size (latency / launch bound)")
 
 
 _REAL_STDOUT = None
@@ -152,32 +257,54 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--dump-kernels", default="")
+    ap.add_argument("--kernels", action="store_true", help="time the bandwidth-bound kernels alone (B = 16384 and B = 128)")
+    ap.add_argument("--gpu-reference-steps", type=int, default=20, help="steps of the reference's eager CUDA path timed beside ours (0: skip)")
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    # `config` is identical in both arms (the driver compares them); everything measured or run-specific goes to `details`
     base = dict(metric=METRIC if a.config in ("c2", "c3") else cfg["workload"].split(",")[0] + " train images/s",
                 unit="images/s", n_gpus=world, higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic",
-                config={"workload": cfg["workload"], "schedule_epoch": EPOCH})
+                config={"workload": cfg["workload"], "schedule_epoch": EPOCH, "batch_per_gpu": "%d labelled + %d unlabelled" % (BATCH, BATCH),
+                        "passes_per_step": 2 if cfg["m2"] else 4,
+                        "l2": "no explicit flush: one step streams ~1.3 GB of saved activations + 150 MB of parameter/optimizer state, > 126 MB L2"})
+
+    if a.kernels:
+        assert torch.cuda.is_available(), "bench.py --kernels needs a CUDA device"
+        _emit(bandwidth_kernels_leg())
+        return
 
     if a.impl == "reference":
         if rank != 0:
             return
-        steps, warm = max(1, min(a.steps, 20)), max(1, min(a.warmup, 2))
-        r = cpu_reference_arm(cfg, steps, warm)
+        # the driver's K and W are honoured; only configurations whose CPU step takes tens of seconds are bounded
+        cap = {"c4": 4}.get(a.config, 10 ** 6)
+        steps, warm = max(1, min(a.steps, cap)), max(0, min(a.warmup, cap))
+        r = cpu_reference_arm(a.config, cfg, steps, warm)
         line = dict(base, impl="reference", value=r["value"], steps=steps, warmup=warm, ms_per_step=r["ms_per_step"], dtype="f32",
-                    n_gpus=0 if world == 1 else world, gpu_launches=0,
+                    n_gpus=world, gpu_launches=0,
                     cpu_baseline=dict(value=r["value"], unit="images/s", cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                     e2e=dict(value=r["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        line["n_gpus"] = world
         _emit(line)
+        return
+
+    if a.impl == "gpu_reference":
+        # the unmodified reference on ONE GPU through torch's eager CUDA path (its own train(), cuDNN TF32 convolutions)
+        if rank != 0:
+            return
+        h = run_ref_harness(a.config, "cuda", a.steps, max(a.warmup, 3), gpu_index=str(local))
+        _emit(dict(base, impl="gpu_reference", **({"unavailable": "baseline/_ref not present"} if h is None else
+                   dict(value=h["images_per_s"], steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=h["ms_per_step"], dtype="tf32",
+                        details=h))))
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (libshotvae has no CPU path)"
     torch.cuda.set_device(local)
     import torch.distributed as dist
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SHOTVAE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL's log (communicator ranks, NVLS / ring choice) goes to stderr: fd 1 is guarded, stdout stays the one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("SHOTVAE_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "INFO"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from shot_vae_model.vae import VariationalAutoEncoder
     from shotvae_b200.engine import TrainStep, default_hyper
@@ -207,19 +334,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    graph_ok = use_graph
-    try:
-        for i in range(3):                      # allocate buffers, then capture the CUDA graph
-            ts.step(*pool[i % len(pool)])
-            log("warm step %d done" % i)
-    except Exception as e:                      # capture refused (e.g. a collective that cannot be captured)
-        if not use_graph:
-            raise
-        torch.cuda.synchronize()
-        graph_ok = False
-        ts.use_graph, ts.graph = False, None
-        base["config"]["graph_fallback"] = repr(e)[:200]
-        ts.step(*pool[0])
+    for i in range(3):                          # two eager steps allocate every buffer, the third captures the CUDA graph
+        ts.step(*pool[i % len(pool)])           # (a capture failure propagates: there is no eager fallback for the timed run)
+        log("warm step %d done" % i)
+    assert (ts.graph is not None) == use_graph, "CUDA graph capture did not happen"
     W = max(a.warmup, 3)
     for i in range(W):
         ts.step(*pool[i % len(pool)])
@@ -291,10 +409,10 @@ def main():
         step_flops = sum(d["flops"] for d in agg.values()) / 3
         roof = dict(bound="tensor", kernel="sv_igemm_fprop family (conv / convT fprop + dgrad: tcgen05 halo-tile and per-tap TMA kernels, "
                                            "mma.sync for strided / C=16 shapes)",
-                    achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                    traffic_source="dram__bytes_read.sum + dram__bytes_write.sum averaged over the family's launches of one step, "
-                                   "profiles/r01_launches_n1_summary.md (ncu, C2, N=1); algorithmic bytes per launch = "
-                                   "hbm.algorithmic_mb_per_step / launches_per_step", peak_source=how + ", sustained bf16",
+                    achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                    traffic_source="not measured in-run (needs ncu): dram__bytes_read.sum + dram__bytes_write.sum per launch of this family is "
+                                   "tabulated in " + TRAFFIC_SOURCE + " (ncu launch list of this command at this commit); algorithmic "
+                                   "bytes per launch = hbm.algorithmic_mb_per_step / launches_per_step", peak_source=how + ", sustained bf16",
                     launches_per_step=f["n"] // 3, avg_launch_us=1e3 * f["ms"] / max(f["n"], 1),
                     algorithmic_gflop_per_step=step_flops / 1e9,
                     hbm=dict(achieved=hbm_ach, peak=hbm_peak, unit="GB/s", frac=(hbm_ach / hbm_peak if hbm_peak else None),
@@ -321,21 +439,28 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None
+    cpu = gpu_ref = None
     if world == 1 and a.cpu_steps > 0:
-        r = cpu_reference_arm(cfg, a.cpu_steps, 1)
+        r = cpu_reference_arm(a.config, cfg, a.cpu_steps if a.config != "c4" else min(a.cpu_steps, 2), 1)
         cpu = dict(value=r["value"], unit="images/s", cores=r["cores"], kind=r["kind"], sample=r["sample"])
+    if world == 1 and a.gpu_reference_steps > 0:
+        # the unmodified reference on this GPU through torch's eager CUDA path, after our own timed regions (separate process:
+        # its `lib` / `shot_vae_model` packages share their names with the drop-in ones)
+        h = run_ref_harness(a.config, "cuda", a.gpu_reference_steps, 5, gpu_index=str(local))
+        if h is not None:
+            gpu_ref = dict(value=h["images_per_s"], unit="images/s", ms_per_step=h["ms_per_step"], steps=h["steps"], warmup=h["warmup"],
+                           kind="unmodified reference (%s), torch %s eager CUDA, cuDNN %s, %s" % (h["entry"], h["torch"], h.get("cudnn"), h.get("precision")),
+                           gpu=h.get("gpu"))
     imgs = world * BATCH * a.steps
     line = dict(base, impl="ours", value=imgs / t_res, steps=a.steps, warmup=W, ms_per_step=1e3 * t_res / a.steps, dtype="bf16",
                 clocks=clocks, gpu_launches=launches * a.steps,
                 e2e=dict(value=imgs / t_e2e, unit="images/s", h2d_bytes_per_step=ts.h2d_bytes(), d2h_bytes_per_step=64,
                          ms_per_step=1e3 * t_e2e / a.steps),
-                roofline=roof, cpu_baseline=cpu)
-    line["config"].update(parallelism="dp%d" % world, passes_per_step=2 if cfg["m2"] else 4, cuda_graph=bool(graph_ok and ts.graph is not None),
-                          launches_per_step=launches, noise="device RNG (torch CUDA generator); lambda / pairing drawn on the host as in the reference",
-                          l2="no explicit flush: one step streams ~1.3 GB of saved activations + 150 MB of parameter/optimizer state, > 126 MB L2",
-                          last_terms={k: round(v, 4) for k, v in (last or {}).items()},
-                          allreduce_bytes_per_step=(reducer.bytes_per_step if reducer else 0))
+                roofline=roof, cpu_baseline=cpu, gpu_reference=gpu_ref)
+    line["details"] = dict(parallelism="dp%d" % world, cuda_graph=bool(ts.graph is not None), launches_per_step=launches,
+                           noise="device RNG (torch CUDA generator); lambda / pairing drawn on the host as in the reference",
+                           last_terms={k: round(v, 4) for k, v in (last or {}).items()},
+                           allreduce_bytes_per_step=(reducer.bytes_per_step if reducer else 0))
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -473,3 +473,114 @@ def synthetic_batch(batch, nd, seed):
     g = torch.Generator().manual_seed(seed)
     return (torch.rand(batch, 3, 32, 32, generator=g), torch.randint(0, nd, (batch,), generator=g),
             torch.rand(batch, 3, 32, 32, generator=g), torch.randint(0, nd, (batch,), generator=g))
+
+
+# ----------------------------------------------------------------------------------------------
+# entry points the reference defines but never calls
+# ----------------------------------------------------------------------------------------------
+def _rec_term(x, x_rec, x_sigma, bce):
+    B = x.size(0)
+    if bce:                                                               # criterion.py:67-68 / 125-126
+        return F.binary_cross_entropy_with_logits(x_rec, x, reduction="sum") / B
+    return F.mse_loss(torch.sigmoid(x_rec), x, reduction="sum") / (2 * B * x_sigma ** 2)   # criterion.py:70-71 / 128-129
+
+
+def _kl_std_normal(mu, ls):
+    return 0.5 * torch.sum(mu * mu + torch.exp(2 * ls) - 2 * ls - 1) / mu.size(0)           # criterion.py:73-76
+
+
+def m1_criterion(x, x_rec, mu, ls, x_sigma=1.0, bce=True):
+    """M1Criterion.forward (criterion.py:64-76)"""
+    return _rec_term(x, x_rec, x_sigma, bce), _kl_std_normal(mu, ls)
+
+
+def m2_criterion(mu, ls, la, nd):
+    """M2Criterion.forward (criterion.py:83-91)"""
+    prior = torch.log(torch.tensor([1 / nd for _ in range(nd)]).view(1, -1).float())
+    return _kl_std_normal(mu, ls), torch.sum(torch.exp(la) * (la - prior)) / mu.size(0)
+
+
+def reconstruction_criterion(x, x_rec, x_sigma=1.0, bce=True):
+    """ReconstructionCriterion.forward (criterion.py:122-131)"""
+    return _rec_term(x, x_rec, x_sigma, bce)
+
+
+def kl_norm_criterion(mu_pre, ls_pre, mu_gt=None, sigma_gt=None):
+    """KLNormCriterion.forward (criterion.py:138-158)"""
+    if mu_gt is None or sigma_gt is None:
+        return _kl_std_normal(mu_pre, ls_pre)
+    v_gt = sigma_gt ** 2
+    return 0.5 * torch.sum(2 * torch.log(sigma_gt + 1e-4) - 2 * ls_pre + torch.exp(2 * ls_pre) / v_gt
+                           + (mu_pre - mu_gt) ** 2 / v_gt - 1) / mu_pre.size(0)
+
+
+def kl_disc_criterion(log_pre, gt, qp_order=True):
+    """KLDiscCriterion.forward (criterion.py:170-177)"""
+    log_gt = torch.log(gt + 1e-4)
+    if qp_order:
+        return torch.sum(torch.exp(log_pre) * (log_pre - log_gt)) / log_pre.size(0)
+    return torch.sum(gt * (log_gt - log_pre)) / log_pre.size(0)
+
+
+def pairwise_norm_kl_dist(u1, ls1, u2, ls2):
+    """pairwise_norm_kl_dist_gpu (calculate_dist.py:94-107)"""
+    v1, v2 = torch.exp(ls1) ** 2, torch.exp(ls2) ** 2
+    ratio = v1.unsqueeze(1) / v2.unsqueeze(0)
+    shift = (u1.unsqueeze(1) - u2.unsqueeze(0)) ** 2 / v2.unsqueeze(0)
+    return 0.5 * (-torch.log(ratio).sum(2) + ratio.sum(2) + shift.sum(2) - ls1.size(1))
+
+
+def pairwise_square_euclidean(v1, v2):
+    """pairwise_square_euclidean_gpu (calculate_dist.py:110-117)"""
+    return ((v1.unsqueeze(1) - v2.unsqueeze(0)) ** 2).sum(2)
+
+
+def pairwise_norm_wasserstein_dist(u1, ls1, u2, ls2):
+    """pairwise_norm_wasserstein_dist_gpu (calculate_dist.py:120-130)"""
+    return pairwise_square_euclidean(u1, u2) + pairwise_square_euclidean(torch.exp(ls1), torch.exp(ls2))
+
+
+def mean_dist_pairwise(u1, u2, distance="euclidean"):
+    """calculate_mean_dist_pairwise (calculate_dist.py:133-160); "cosine" divides by squared norms as written"""
+    if distance == "euclidean":
+        return pairwise_square_euclidean(u1, u2)
+    if distance == "cosine":
+        return torch.mm(u1, u2.t()) / ((u1 ** 2).sum(1).view(-1, 1) * (u2 ** 2).sum(1).view(1, -1))
+    raise NotImplementedError("distance {} not implemented".format(distance))
+
+
+# ----------------------------------------------------------------------------------------------
+# input pipeline (reference lib/dataloader.py; SURVEY.md section 8 row f4)
+# ----------------------------------------------------------------------------------------------
+def augment_batch(data, index, params, pad=4, out_size=32, hwc=True):
+    """The reference's train transform Pad(pad, reflect) -> RandomHorizontalFlip -> RandomCrop(out_size) -> ToTensor
+    (dataloader.py:42-70) for given per-sample parameters params[b] = (crop row, crop column, flip); params None =
+    the test transform (ToTensor only).  data: uint8 numpy [N, H, W, C] (hwc) or [N, C, H, W]; -> float32 [B, C, out, out]."""
+    data = np.asarray(data)
+    outs = []
+    for b, i in enumerate(np.asarray(index).tolist()):
+        img = data[i] if hwc else np.transpose(data[i], (1, 2, 0))        # H, W, C
+        ci, cj, flip = (0, 0, 0) if params is None else [int(v) for v in params[b]]
+        p = pad if params is not None else 0
+        img = np.pad(img, ((p, p), (p, p), (0, 0)), mode="reflect") if p else img   # transforms.Pad(padding_mode='reflect')
+        if flip:
+            img = img[:, ::-1]                                               # RandomHorizontalFlip on the padded image
+        img = img[ci:ci + out_size, cj:cj + out_size]                        # RandomCrop
+        outs.append(np.transpose(img, (2, 0, 1)).astype(np.float32) / np.float32(255.0))   # ToTensor
+    return torch.from_numpy(np.stack(outs))
+
+
+def per_class_split(labels, num_classes, valid_num_per_class, annotated_num_per_class=None):
+    """get_ssl_sampler / get_cifar10_sl_sampler index lists (dataloader.py:73-92,115-139): per class one
+    torch.randperm over its positions; valid = first v, labelled = next a, unlabelled / train = everything after v.
+    -> (valid, train_l, train_u) or (valid, train) when annotated_num_per_class is None."""
+    v, a = valid_num_per_class, annotated_num_per_class
+    valid, lab, rest = [], [], []
+    for c in range(num_classes):
+        loc = torch.nonzero(labels == c).view(-1)
+        loc = loc[torch.randperm(loc.size(0))]
+        valid.extend(loc[:v].tolist())
+        if a is not None:
+            lab.extend(loc[v:v + a].tolist())
+        rest.extend(loc[v:].tolist())
+    return (valid, rest) if a is None else (valid, lab, rest)

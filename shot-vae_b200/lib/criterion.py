@@ -147,27 +147,41 @@ class M2Criterion(nn.Module):
         return _KLFn.apply(M2_mean, M2_log_sigma, disc_log_alpha)
 
 
+class _KLPairFn(torch.autograd.Function):
+    """two-distribution KL forms (criterion.py:151-157,172-176): loss and every input gradient in one pass"""
+
+    @staticmethod
+    def forward(ctx, mode, *xs):
+        xs = [x.contiguous().float() for x in xs]
+        _need_cuda(*xs)
+        batch = xs[0].size(0)
+        loss = torch.zeros(1, dtype=torch.float32, device=xs[0].device)
+        grads = [torch.empty_like(x) if ctx.needs_input_grad[i + 1] else None for i, x in enumerate(xs)]
+        pad = [None] * (4 - len(xs))
+        check(lib.sv_kl_pair_fwd_bwd(mode, *[ptr(x) for x in xs + pad], xs[0].numel(), batch, ptr(loss),
+                                     *[ptr(g) for g in grads + pad], _abi.stream()))
+        ctx.grads = grads
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, go):
+        return (None,) + tuple(None if g is None else g * go for g in ctx.grads)
+
+
 class KLNormCriterion(nn.Module):
-    """criterion.py:134-158.  The prior form uses the fused kernel; the two-Gaussian form is not on any
-    path of the reference and is expressed with torch ops on the caller's device."""
+    """criterion.py:134-158 (never called by the reference): KL to the standard normal through the fused ELBO-KL
+    kernel, KL between two diagonal Gaussians through sv_kl_pair_fwd_bwd."""
 
     def forward(self, z_mean_pre, z_log_sigma_pre, z_mean_gt=None, z_sigma_gt=None):
-        batch_size = z_mean_pre.size(0)
         if z_mean_gt is None or z_sigma_gt is None:
-            dummy = torch.full((batch_size, 2), -0.6931471805599453, device=z_mean_pre.device)
+            dummy = torch.full((z_mean_pre.size(0), 2), -0.6931471805599453, device=z_mean_pre.device)
             return _KLFn.apply(z_mean_pre, z_log_sigma_pre, dummy)[0]
-        ls2_pre = 2 * z_log_sigma_pre
-        ls2_gt = 2 * torch.log(z_sigma_gt + 1e-4)
-        s2_gt = z_sigma_gt ** 2
-        return 0.5 * torch.sum(ls2_gt - ls2_pre + torch.exp(ls2_pre) / s2_gt + (z_mean_pre - z_mean_gt) ** 2 / s2_gt - 1) / batch_size
+        return _KLPairFn.apply(0, z_mean_pre, z_log_sigma_pre, z_mean_gt, z_sigma_gt)
 
 
 class KLDiscCriterion(nn.Module):
-    """criterion.py:161-177 (never called by the reference)."""
+    """criterion.py:161-177 (never called by the reference): sum_j KL between predicted log-probabilities and target
+    probabilities, in either order."""
 
     def forward(self, disc_log_pre, disc_gt, qp_order=True):
-        batch_size = disc_log_pre.size(0)
-        disc_log_gt = torch.log(disc_gt + 1e-4)
-        if qp_order:
-            return torch.sum(torch.exp(disc_log_pre) * (disc_log_pre - disc_log_gt)) / batch_size
-        return torch.sum(disc_gt * (disc_log_gt - disc_log_pre)) / batch_size
+        return _KLPairFn.apply(1 if qp_order else 2, disc_log_pre, disc_gt)

@@ -1,0 +1,279 @@
+"""GPU parity tests for the rows beside the training step and the regressions the round-1
+review asked for: kernel-backed criteria / distance helpers / device input pipeline against the CPU oracle, a
+forward after optimizer.step() (packed operand copies must follow the FP32 masters), eval forwards between fused
+steps, optimizer-state checkpointing of the fused engine and batches that change size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_gpu_step import build_model, rel, shot_loop_body, _oracle_step_with_sgd, _feed, grad_errors
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_rms(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------- f3
+def test_unused_criteria_match_oracle():
+    from oracle import shotvae_oracle as O
+    from lib import criterion as Cr
+    from tests.golden.make_golden_aux import aux_inputs
+    d, nd = aux_inputs()
+    c = {k: v.cuda() for k, v in d.items()}
+    chk = lambda got, want: abs(float(got) - float(want)) <= 2e-5 * max(1.0, abs(float(want)))
+    for bce, sig in ((True, 1), (False, 0.5)):
+        for g, w in zip(Cr.M1Criterion(sig, bce)(c["x"], c["x_rec"], c["mu"], c["ls"]), O.m1_criterion(d["x"], d["x_rec"], d["mu"], d["ls"], sig, bce)):
+            assert chk(g, w)
+        assert chk(Cr.ReconstructionCriterion(sig, bce)(c["x"], c["x_rec"]), O.reconstruction_criterion(d["x"], d["x_rec"], sig, bce))
+    for g, w in zip(Cr.M2Criterion(nd)(c["mu"], c["ls"], c["la"]), O.m2_criterion(d["mu"], d["ls"], d["la"], nd)):
+        assert chk(g, w)
+    assert chk(Cr.KLNormCriterion()(c["mu"], c["ls"]), O.kl_norm_criterion(d["mu"], d["ls"]))
+    # two-distribution forms: value and every input gradient
+    xs = [d[k].clone().requires_grad_(True) for k in ("mu", "ls", "mu_gt", "sigma_gt")]
+    want = O.kl_norm_criterion(*xs)
+    (want * 1.7).backward()
+    gs = [d[k].cuda().requires_grad_(True) for k in ("mu", "ls", "mu_gt", "sigma_gt")]
+    got = Cr.KLNormCriterion()(*gs)
+    (got * 1.7).backward()
+    assert chk(got, want)
+    for a, b in zip(gs, xs):
+        assert rel_rms(a.grad, b.grad) < 1e-5
+    for order in (True, False):
+        ys = [d[k].clone().requires_grad_(True) for k in ("la", "p_gt")]
+        want = O.kl_disc_criterion(ys[0], ys[1], order)
+        want.backward()
+        gy = [d[k].cuda().requires_grad_(True) for k in ("la", "p_gt")]
+        got = Cr.KLDiscCriterion()(gy[0], gy[1], order)
+        got.backward()
+        assert chk(got, want)
+        for a, b in zip(gy, ys):
+            assert rel_rms(a.grad, b.grad) < 1e-5
+
+
+def test_distance_helpers_match_oracle():
+    from oracle import shotvae_oracle as O
+    from lib.utils import calculate_dist as CD
+    torch.manual_seed(21)
+    u1, ls1, u2, ls2 = torch.randn(37, 128), torch.randn(37, 128) * 0.3, torch.randn(50, 128), torch.randn(50, 128) * 0.3
+    c = [t.cuda() for t in (u1, ls1, u2, ls2)]
+    assert rel_rms(CD.pairwise_norm_kl_dist_gpu(*c), O.pairwise_norm_kl_dist(u1, ls1, u2, ls2)) < 1e-5
+    assert rel_rms(CD.pairwise_square_euclidean_gpu(c[0], c[2]), O.pairwise_square_euclidean(u1, u2)) < 1e-5
+    assert rel_rms(CD.pairwise_norm_wasserstein_dist_gpu(*c), O.pairwise_norm_wasserstein_dist(u1, ls1, u2, ls2)) < 1e-5
+    assert rel_rms(CD.calculate_mean_dist_pairwise(u1.numpy(), u2.numpy(), True, "cosine"), O.mean_dist_pairwise(u1, u2, "cosine")) < 1e-5
+    assert rel_rms(CD.calculate_mean_dist_pairwise(c[0], c[2], True, "euclidean"), O.mean_dist_pairwise(u1, u2, "euclidean")) < 1e-5
+    assert rel_rms(CD.gaussian_kl_calculation_vec(u1.numpy(), ls1.numpy(), True), O.pairwise_norm_kl_dist(u1, ls1, u1, ls1)) < 1e-5
+    # host NumPy branches agree with the device branches
+    assert rel_rms(torch.from_numpy(CD.gaussian_kl_calculation_vec_pairwise(u1.numpy(), ls1.numpy(), u2.numpy(), ls2.numpy())),
+                   O.pairwise_norm_kl_dist(u1, ls1, u2, ls2)) < 1e-5
+    # the authors' vectorised KL selects the same --om partner as the pairing kernel
+    from lib.utils.mixup import optimal_match_index
+    kl = CD.pairwise_norm_kl_dist_gpu(c[0], c[1], c[0], c[1])
+    assert torch.topk(kl, 2, largest=False)[1][:, 1].tolist() == optimal_match_index(c[0], c[1]).tolist()
+    with pytest.raises(NotImplementedError):
+        CD.calculate_mean_dist_pairwise(c[0], c[2], True, "manhattan")
+
+
+# ---------------------------------------------------------------------------------------------- f4
+def test_augment_kernel_bit_exact_vs_oracle():
+    from oracle import shotvae_oracle as O
+    from lib.dataloader import DeviceImageDataset
+    rng = np.random.RandomState(8)
+    data = rng.randint(0, 256, size=(40, 32, 32, 3), dtype=np.uint8)
+    targets = rng.randint(0, 10, size=40)
+    ds = DeviceImageDataset(data, targets, train_flag=True)
+    index = torch.tensor(rng.randint(0, 40, size=33), dtype=torch.int64)
+    params = torch.tensor(np.stack([rng.randint(0, 9, 33), rng.randint(0, 9, 33), rng.randint(0, 2, 33)], 1), dtype=torch.int32)
+    params[0] = torch.tensor([0, 0, 1]); params[1] = torch.tensor([8, 8, 0]); params[2] = torch.tensor([8, 0, 1])
+    img, lab = ds.batch(index.cuda(), params=params.cuda())
+    want = O.augment_batch(data, index.numpy(), params.numpy())
+    assert torch.equal(img.cpu(), want)                                   # bit-exact: uint8 / 255 in fp32
+    assert lab.cpu().tolist() == [int(targets[i]) for i in index.tolist()]
+    # test transform (ToTensor only), SVHN storage (CHW) and MNIST (28x28 -> pad 4 -> crop 32, one channel)
+    te = DeviceImageDataset(data, targets, train_flag=False)
+    assert torch.equal(te.batch(index.cuda())[0].cpu(), O.augment_batch(data, index.numpy(), None))
+    chw = np.ascontiguousarray(data.transpose(0, 3, 1, 2))
+    sv = DeviceImageDataset(chw, targets, train_flag=True, hwc=False)
+    assert torch.equal(sv.batch(index.cuda(), params=params.cuda())[0].cpu(), want)
+    mn = rng.randint(0, 256, size=(9, 28, 28, 1), dtype=np.uint8)
+    md = DeviceImageDataset(mn, list(range(9)), train_flag=False, pad_always=True)
+    mi = torch.arange(9)
+    mp = torch.tensor(np.stack([rng.randint(0, 5, 9), rng.randint(0, 5, 9), np.zeros(9, dtype=np.int64)], 1), dtype=torch.int32)
+    assert torch.equal(md.batch(mi.cuda(), params=mp.cuda())[0].cpu(), O.augment_batch(mn, mi.numpy(), mp.numpy(), pad=4, out_size=32))
+    # drawn parameters stay in range, and a single-sample __getitem__ works
+    p = ds.draw_params(4096)
+    assert int(p[:, :2].min()) >= 0 and int(p[:, :2].max()) <= 8 and set(p[:, 2].unique().tolist()) <= {0, 1}
+    assert 0.3 < float(p[:, 2].float().mean()) < 0.7
+    one, y = ds[3]
+    assert one.shape == (3, 32, 32) and y == int(targets[3])
+
+
+def test_device_loader_epoch_semantics():
+    """SubsetRandomSampler order, short last batch (45 000 / 128 leaves a tail in the reference, main_shot_vae.py:280),
+    labels travel with their images, and every sampled index appears exactly once per epoch"""
+    from lib.dataloader import DeviceImageDataset, DeviceLoader, get_cifar10_ssl_sampler
+    rng = np.random.RandomState(2)
+    n = 700
+    data = np.zeros((n, 32, 32, 3), dtype=np.uint8)
+    data[:, 0, 0, 0] = np.arange(n) % 251                          # a recoverable tag in pixel (0,0) -- only valid without augmentation
+    data[:, 0, 0, 1] = np.arange(n) // 251
+    targets = rng.randint(0, 10, size=n)
+    ds = DeviceImageDataset(data, targets, train_flag=False)
+    torch.manual_seed(4)
+    sv, sl, su = get_cifar10_ssl_sampler(torch.tensor(targets, dtype=torch.int32), 5, 8, 10)
+    loader = DeviceLoader(ds, batch_size=128, sampler=su)
+    assert len(loader) == (len(su) + 127) // 128
+    seen = []
+    sizes = []
+    for img, lab in loader:
+        assert img.is_cuda and lab.is_cuda and img.dtype == torch.float32 and lab.dtype == torch.int64
+        ids = (img[:, 0, 0, 0] * 255).round().long() + 251 * (img[:, 1, 0, 0] * 255).round().long()
+        assert lab.cpu().tolist() == [int(targets[i]) for i in ids.cpu().tolist()]
+        seen.extend(ids.cpu().tolist())
+        sizes.append(img.size(0))
+    assert sorted(seen) == sorted(su.indices) and sizes[:-1] == [128] * (len(sizes) - 1) and sizes[-1] == len(su) - 128 * (len(sizes) - 1)
+    again = [i for img, _ in loader for i in ((img[:, 0, 0, 0] * 255).round().long() + 251 * (img[:, 1, 0, 0] * 255).round().long()).cpu().tolist()]
+    assert sorted(again) == sorted(seen) and again != seen          # a fresh permutation every epoch
+
+
+# ------------------------------------------------------------------------------- review regressions
+def test_forward_after_optimizer_step_uses_updated_weights():
+    """forward, optimizer.step(), forward -- the bf16 operand copies of the conv weights must be
+    re-derived, and two reference-style steps (torch.optim.SGD on the drop-in modules) must track the oracle's two steps"""
+    from oracle import shotvae_oracle as O
+    from lib.criterion import VAECriterion, ClsCriterion
+    net, nd, B, epoch = "wideresnet-10-1", 10, 16, 100
+    hyper = O.default_hyper("Cifar10")
+    s = O.schedules(hyper, epoch)
+    st, ost, (il, ll, iu, lu), outs, logs = _oracle_step_with_sgd(net, nd, B, epoch, hyper, 5, 11, nsteps=2)
+    model = build_model(net, nd, st).train()
+    opt = torch.optim.SGD(model.parameters(), lr=hyper["lr"], momentum=hyper["momentum"], weight_decay=hyper["wd"])
+    crit, cls = VAECriterion(nd, hyper["x_sigma"], True).cuda(), ClsCriterion()
+    torch.manual_seed(5); np.random.seed(5)
+    with torch.no_grad():
+        torch.manual_seed(99)
+        before = model(iu.cuda())[0].clone()
+    torch.manual_seed(5); np.random.seed(5)
+    got = []
+    for i in range(2):
+        got.append(shot_loop_body(model, crit, cls, il.cuda(), ll.cuda(), iu.cuda(), lu.cuda(), s, nd, False, hyper["epsilon"]))
+        opt.step()
+        opt.zero_grad()
+    with torch.no_grad():
+        torch.manual_seed(99)
+        after = model(iu.cuda())[0]
+    assert rel(after, before) > 1e-3, "the forward after optimizer.step() still used the initial conv weights"
+    for k in ("rec_l", "klc_l", "rec_u", "klc_u"):
+        assert abs(got[0][k] - outs[0][k]) < 1e-3 * abs(outs[0][k]), (k, got[0][k], outs[0][k])
+        # the second step runs on UPDATED weights: with stale conv weights rec stays at its step-1 value (~2420 -> ~2300 here)
+        assert abs(got[1][k] - outs[1][k]) < 2e-2 * abs(outs[1][k]), (k, got[1][k], outs[1][k])
+    sd = model.state_dict()
+    errs = grad_errors({k: sd[k].float().cpu() - st[k].float() for k in O.param_names(ost)},
+                       {k: ost[k].detach().float() - st[k].float() for k in O.param_names(ost)})
+    assert errs["decoder"] < 0.2 and errs["heads"] < 0.2, errs
+    # load_state_dict after a forward must also repack
+    model.load_state_dict(st)
+    with torch.no_grad():
+        torch.manual_seed(99)
+        again = model(iu.cuda())[0]
+    # (two runs of the same train-mode forward differ by the summation order of the statistics atomics, amplified by the bf16 net)
+    assert rel(again, before) < 2e-2 and rel(again, before) < 0.2 * rel(after, before), (rel(again, before), rel(after, before))
+
+
+def test_eval_forward_between_fused_steps_sees_current_weights():
+    """a model.eval() forward after TrainStep.step() must not run on conv weights that are one SGD step stale"""
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    net, nd, B, epoch = "wideresnet-10-1", 10, 16, 100
+    hyper = O.default_hyper("Cifar10")
+    st, ost, (il, ll, iu, lu), outs, logs = _oracle_step_with_sgd(net, nd, B, epoch, hyper, 5, 11, nsteps=1)
+    model = build_model(net, nd, st).train()
+    ts = TrainStep(model, B, hyper=hyper, use_graph=False, device_noise=False)
+    ts.set_epoch(epoch)
+    ts.step(il, ll, iu, lu, draws=_feed(ts, logs[0], False))
+    model.eval()
+    torch.manual_seed(7)
+    with torch.no_grad():
+        got = model(iu.cuda(), disc_label=lu.cuda())
+    torch.manual_seed(7)
+    with torch.no_grad():
+        want = O.vae_forward(ost, O.encoder_topology(net), iu, O.LiveDraws(), 0.67, disc_label=lu, training=False)
+    errs = {n: rel(a, b) for n, a, b in zip(("rec", "mu", "ls", "la"), got, want)}
+    # against the oracle's POST-step state; with stale (pre-step) conv weights rec is off by > 0.3 here
+    assert max(errs.values()) < 6e-2, errs
+    torch.manual_seed(7)
+    with torch.no_grad():
+        stale = O.vae_forward(O.clone_state(st), O.encoder_topology(net), iu, O.LiveDraws(), 0.67, disc_label=lu, training=False)
+    assert rel(got[0], stale[0]) > 2 * errs["rec"]
+
+
+# ---------------------------------------------------------------------------------------------- f2
+def test_fused_optimizer_state_roundtrip_and_resume():
+    """TrainStep.state_dict() is a torch.optim.SGD state dict (the reference checkpoints 'optimizer', main_shot_vae.py:241);
+    a run resumed from {model.state_dict(), step.state_dict()} continues exactly like the uninterrupted one, and a plain
+    torch.optim.SGD state dict loads into the fused engine."""
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    net, nd, B = "wideresnet-10-1", 10, 16
+    hyper = O.default_hyper("Cifar10")
+    st = O.init_state(net, nd)
+    il, ll, iu, lu = O.synthetic_batch(B, nd, 3)
+    g = torch.Generator().manual_seed(1)
+    feeds = [(torch.randn(4, B, 128, generator=g), torch.rand(2, B, nd, generator=g),
+              (0.95, torch.randperm(B, generator=g), 0.4 + 0.1 * i, torch.randperm(B, generator=g))) for i in range(4)]
+
+    def run(ts, i):
+        ts.set_noise(feeds[i][0].cuda(), feeds[i][1].cuda())
+        return ts.step(il, ll, iu, lu, draws=feeds[i][2])
+
+    ma = build_model(net, nd, st).train()
+    ta = TrainStep(ma, B, hyper=hyper, use_graph=False, device_noise=False)
+    ta.set_epoch(50)
+    for i in range(2):
+        run(ta, i)
+    ckpt = {"state_dict": {k: v.clone() for k, v in ma.state_dict().items()}, "optimizer": ta.state_dict()}
+    # it IS a torch SGD state dict
+    probe = torch.optim.SGD(build_model(net, nd, st).parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    probe.load_state_dict({k: v for k, v in ckpt["optimizer"].items() if k != "shotvae"})
+    assert len(probe.state_dict()["state"]) == len(list(ma.parameters()))
+    for i in range(2, 4):
+        ra = run(ta, i)
+    mb = build_model(net, nd, ckpt["state_dict"]).train()
+    tb = TrainStep(mb, B, hyper=hyper, use_graph=False, device_noise=False)
+    tb.set_epoch(50)
+    tb.load_state_dict(ckpt["optimizer"])
+    for i in range(2, 4):
+        rb = run(tb, i)
+    for k in ("rec_l", "klc_l", "rec_u", "disc_post_u"):
+        assert abs(ra[k] - rb[k]) <= 2e-3 * abs(ra[k]), (k, ra[k], rb[k])       # only the atomics' summation order differs
+    sa, sb = ma.state_dict(), mb.state_dict()
+    errs = grad_errors({k: sb[k].float() for k in sa if sa[k].dtype == torch.float32 and "running" not in k},
+                       {k: sa[k].float() for k in sa if sa[k].dtype == torch.float32 and "running" not in k})
+    assert errs["all"] < 5e-3, errs
+    # without the momentum state the resumed run is measurably different (the test would catch a no-op load)
+    mc = build_model(net, nd, ckpt["state_dict"]).train()
+    tc = TrainStep(mc, B, hyper=hyper, use_graph=False, device_noise=False)
+    tc.set_epoch(50)
+    for i in range(2, 4):
+        run(tc, i)
+    sc = mc.state_dict()
+    errs_c = grad_errors({k: sc[k].float() for k in sa if sa[k].dtype == torch.float32 and "running" not in k},
+                         {k: sa[k].float() for k in sa if sa[k].dtype == torch.float32 and "running" not in k})
+    assert errs_c["all"] > 3 * errs["all"], (errs_c, errs)
+    # a reference-side torch.optim.SGD state dict (after one reference-style step) loads into the fused engine
+    md = build_model(net, nd, st).train()
+    opt = torch.optim.SGD(md.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    rec, mu, ls, la = md(il.cuda(), disc_label=ll.cuda())
+    (rec.sum() * 1e-3 + mu.sum() + la.sum()).backward()
+    opt.step()
+    td = TrainStep(md, B, hyper=hyper, use_graph=False, device_noise=False)
+    td.load_state_dict(opt.state_dict())
+    k0 = "continuous_inference.mean.fc.weight"
+    o, n, shp = md._net.poff[k0]
+    assert torch.equal(md._net.momentum[o:o + n].view(shp), opt.state_dict()["state"][list(dict(md.named_parameters())).index(k0)]["momentum_buffer"])
+    assert float(td.sgd_hyper[4]) == 0.0
