@@ -13,7 +13,7 @@ from oracle import shotvae_oracle as O
 from tests.golden.make_golden import sample_positions
 
 _ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.json")))
-GOLD = [p for p in _ALL if not os.path.basename(p).startswith("eval_")]
+GOLD = [p for p in _ALL if not os.path.basename(p).startswith(("eval_", "aux_"))]      # aux_*: tests/test_aux_cpu.py
 GOLD_EVAL = [p for p in _ALL if os.path.basename(p).startswith("eval_")]
 RTOL = 1e-5
 
