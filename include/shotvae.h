@@ -59,6 +59,18 @@ typedef struct {
   int32_t impl;         /* 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 + per-tap TMA kernel,
                            3 = tcgen05 halo-tile kernel (input read once, taps = shifted descriptors) */
   int32_t w_layout;     /* layout of Wt: 0 = [T][N][C]; 1 = [T][C/8][N][8] (required by, and selects, kernel 3) */
+  /* Fused BatchNorm-backward statistics (input-gradient launches): when bn_y != NULL the output IS the gradient
+   * w.r.t. the activated tensor a = act(scale*y + shift) of the BatchNorm whose input y (bf16, layout of out_bf16)
+   * and per-group coefficients [G][N] are given here, and instead of sum / sum-of-squares the epilogue accumulates
+   *   stats[0][g][n] += sum dz            (d loss / d beta),   dz = out * (scale*y + shift > 0 ? 1 : bn_slope)
+   *   stats[1][g][n] += sum dz * x_hat    (d loss / d gamma),  x_hat = (y - mean) * rsqrt(var + bn_eps)
+   * (note the [2][G][N] layout).  Kernels 2 and 3 only; residual must be NULL. */
+  const void* bn_y;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_var;
+  float bn_slope, bn_eps;
 } sv_igemm_args;
 int sv_igemm_fprop(const sv_igemm_args* a, void* stream);
 /* 1 if kernel `impl` (1, 2, 3) can run this problem; impl = 0 returns the kernel auto mode selects */

@@ -66,6 +66,12 @@ static int fill_params(const sv_igemm_args* a, IgemmParams& p) {
   p.rows_per_group = a->group_images * a->OH * a->OW;
   p.w_layout = a->w_layout;
   memcpy(p.dy, a->dy, SV_MAX_TAPS); memcpy(p.dx, a->dx, SV_MAX_TAPS);
+  p.bn_y = (const bf16*)a->bn_y; p.bn_scale = a->bn_scale; p.bn_shift = a->bn_shift; p.bn_mean = a->bn_mean; p.bn_var = a->bn_var;
+  p.bn_slope = a->bn_slope; p.bn_eps = a->bn_eps;
+  if (p.bn_y != nullptr) {
+    SV_REQUIRE(p.stats && p.bn_scale && p.bn_shift && p.bn_mean && p.bn_var, "sv_igemm_fprop: fused BatchNorm-backward statistics need stats + coefficients");
+    SV_REQUIRE(p.res == nullptr && p.out != nullptr && p.outf == nullptr, "sv_igemm_fprop: fused BatchNorm-backward statistics: bf16 output, no residual");
+  }
   return SV_OK;
 }
 
@@ -90,8 +96,11 @@ static int select_impl(const IgemmParams& p) {
 int sv_igemm_fprop_supports(const sv_igemm_args* a, int32_t impl) {
   IgemmParams p;
   if (fill_params(a, p) != SV_OK) return 0;
-  if (impl == 0) return select_impl(p);
-  if (impl == 1) return p.w_layout == 0 ? 1 : 0;
+  if (impl == 0) {
+    const int sel = select_impl(p);
+    return (p.bn_y != nullptr && sel == 1) ? 0 : sel;      // the mma.sync kernel has no fused BatchNorm-backward epilogue
+  }
+  if (impl == 1) return (p.w_layout == 0 && p.bn_y == nullptr) ? 1 : 0;
 #ifndef SV_NO_TCGEN05
   if (impl == 2) return igemm_fprop_tc_supported(p) ? 1 : 0;
   if (impl == 3) return igemm_fprop_halo_supported(p) ? 1 : 0;
@@ -117,6 +126,7 @@ int sv_igemm_fprop(const sv_igemm_args* a, void* stream) {
   }
 #endif
   SV_REQUIRE(impl == 1, "sv_igemm_fprop: unknown impl %d", impl);
+  SV_REQUIRE(p.bn_y == nullptr, "sv_igemm_fprop: fused BatchNorm-backward statistics are not available on the mma.sync kernel");
   SV_REQUIRE(p.w_layout == 0, "sv_igemm_fprop: plane-interleaved weights are only consumed by the halo kernel");
   return igemm_fprop_mma(p, st);
 }

@@ -20,7 +20,29 @@ struct IgemmParams {
   int w_layout;        // 0 = [T][N][C], 1 = [T][C/8][N][8]
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
+  // fused BatchNorm-backward statistics (see sv_igemm_args)
+  const bf16* bn_y;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_var;
+  float bn_slope, bn_eps;
 };
+
+// Epilogue helper shared by the tcgen05 kernels: coef = {scale, shift, rstd, -mean*rstd} of 4 consecutive channels.
+// v: output-gradient values (already rounded to bf16) -> dz in v, dz * x_hat in w.
+__device__ __forceinline__ void bn_bwd_terms4(const float* yv, const float4 sc, const float4 sh, const float4 rs, const float4 mr,
+                                              float slope, float* v, float* w) {
+  const float s[4] = {sc.x, sc.y, sc.z, sc.w}, h[4] = {sh.x, sh.y, sh.z, sh.w}, r[4] = {rs.x, rs.y, rs.z, rs.w},
+              m[4] = {mr.x, mr.y, mr.z, mr.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float pre = fmaf(yv[j], s[j], h[j]);
+    const float dz = pre > 0.f ? v[j] : slope * v[j];
+    v[j] = dz;
+    w[j] = dz * fmaf(yv[j], r[j], m[j]);
+  }
+}
 
 struct WgradParams {
   const bf16* A;

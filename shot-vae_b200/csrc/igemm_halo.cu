@@ -19,8 +19,8 @@
 // The A tile is therefore staged by three producer warps with zero-filling 16-byte cp.async (global
 // reads fully coalesced: one image row = W*C*2 contiguous bytes), published to the tensor core with
 // cp.async.mbarrier.arrive.noinc + a consumer-side fence.proxy.async; the resident weights arrive by 1-D bulk
-// copies (cp.async.bulk).  The staged (shared memory + bulk store) epilogue behind SHOTVAE_HALO_STAGE=1 is an
-// experiment that measured slower than the direct 32-byte stores and is off by default.
+// copies (cp.async.bulk).  (A shared-memory staged, bulk-store epilogue was measured ~35 % slower than the direct 32-byte
+// stores in round 1 and has been removed.)
 //
 // warp roles (12 warps = 3 per scheduler, so every thread may use 168 registers): 0..3 and 8..11 = epilogue
 // (TMEM -> registers -> +bias/+residual -> bf16 NHWC 32-byte stores, BatchNorm sum / sum^2), 4..6 = A-tile
@@ -46,6 +46,11 @@ constexpr int MAX_GROUPS = 4;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_ACC = 8;      // TMEM accumulator ring (the commit -> epilogue signal lags the MMAs by 1-4k cycles under store traffic)
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
+#ifdef SV_HALO_TRACE
+constexpr bool kTrace = true;    // debug build: clock64 timeline of CTA 0 + role ablation (tools/halo_trace.py, tools/halo_lag.py)
+#else
+constexpr bool kTrace = false;   // production build: the instrumentation is compiled out of every role loop
+#endif
 constexpr int PAD_SLOTS = 8;   // slack slots (128 B) in front of the A tile: tap (-1,-1) of slot 0 reads 1 slot before it
 
 struct HaloParams {
@@ -64,11 +69,16 @@ struct HaloParams {
   int one_commit;           // the epilogue releases the A stage (one tcgen05.commit per tile instead of two)
   int planes, planes_log2, chunks_per_row;
   int trace, ablate, lag;
-  int staged;               // epilogue goes through shared memory + bulk copies (contiguous output rows)
-  uint32_t stg_off;         // byte offset of the two staging buffers inside dynamic smem
   uint32_t inv_P;           // ceil(65536 / P): s / P == (s * inv_P) >> 16 for the slot range used here
   const bf16* A;
   const bf16* Wp;           // weights packed [T][C/8][N][8]
+  // fused BatchNorm-backward statistics (input-gradient launches, see sv_igemm_args): y + coefficients [G][N]
+  const bf16* bn_y;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_var;
+  float bn_slope, bn_eps;
   uint32_t a_stage_bytes, a_plane_bytes, b_bytes, b_tap_bytes, b_plane_bytes;
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
@@ -108,12 +118,6 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -149,13 +153,16 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-template <int T_, int KC_>
+// BNB_: the epilogue accumulates BatchNorm-backward statistics (input-gradient launches) instead of sum / sum of squares;
+// a template parameter so that the forward instantiations keep their register allocation
+template <int T_, int KC_, bool BNB_>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 igemm_halo_kernel(const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[MAX_ACC], tmem_empty[MAX_ACC], b_bar, res_bar[2];
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[MAX_ACC], tmem_empty[MAX_ACC], b_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_stat[MAX_GROUPS][2][128];
+  __shared__ __align__(16) float s_coef[BNB_ ? MAX_GROUPS : 1][4][128];     // {scale, shift, rstd, -mean*rstd} of this CTA's channel slice
 
   const long long t_entry = clock64();
   pdl_trigger();
@@ -172,7 +179,6 @@ igemm_halo_kernel(const HaloParams p) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], PRODUCERS); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < p.n_acc; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     mbar_init(&b_bar, 1);
-    mbar_init(&res_bar[0], 1); mbar_init(&res_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < MAX_GROUPS * 2 * 128; i += HL_THREADS) (&s_stat[0][0][0])[i] = 0.f;
@@ -199,7 +205,7 @@ igemm_halo_kernel(const HaloParams p) {
   const uint32_t tmem_base = tmem_base_s;
   // everything above touched only shared / tensor memory and overlapped the previous kernel's tail
   pdl_wait();
-  if (p.trace && blockIdx.x == 0 && tid == 0) { g_halo_marks[0] = t_entry; g_halo_marks[1] = clock64(); }
+  if (kTrace && p.trace && blockIdx.x == 0 && tid == 0) { g_halo_marks[0] = t_entry; g_halo_marks[1] = clock64(); }
 
   if (warp >= 4 && warp < MMA_WARP) {
     // ===================================== A-tile producers (4 warps) =======================
@@ -214,7 +220,7 @@ igemm_halo_kernel(const HaloParams p) {
       const int s0 = p.P + BM * j;              // first output slot of the tile (padded-grid slot index)
       const int y0 = (int)(((uint32_t)s0 * p.inv_P) >> 16) - 1;   // first padded row held in shared memory
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (p.trace && blockIdx.x == 0 && ptid == 0 && it < 64) g_halo_trace[0][it][0] = clock64();
+      if (kTrace && p.trace && blockIdx.x == 0 && ptid == 0 && it < 64) g_halo_trace[0][it][0] = clock64();
       const uint32_t abase = smem_u32(smem_a) + (uint32_t)stage * p.a_stage_bytes + PAD_SLOTS * 16;
       const bf16* img_base = Ag + (size_t)img * p.H * row_elems;
       for (int ch = ptid; ch < p.chunks_per_row; ch += PRODUCERS) {
@@ -225,7 +231,7 @@ igemm_halo_kernel(const HaloParams p) {
 #pragma unroll 4
         for (int r = 0; r < p.R; ++r, ++yu, dst += (uint32_t)p.P * 16, src += row_elems) {
           const bool ok = yu >= 0 && yu < p.H;
-          const int sz = (ok && !(p.ablate & 1)) ? 16 : 0;
+          const int sz = (ok && !(kTrace && (p.ablate & 1))) ? 16 : 0;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(ok ? src : Ag), "r"(sz));
         }
       }
@@ -233,7 +239,7 @@ igemm_halo_kernel(const HaloParams p) {
       // never waits on memory (a wait_group + fence.proxy.async here compiles to MEMBAR.ALL.CTA, which
       // drains every copy in flight and serialises the pipeline on DRAM latency)
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
-      if (p.trace && blockIdx.x == 0 && ptid == 0 && it < 64) g_halo_trace[0][it][1] = clock64();
+      if (kTrace && p.trace && blockIdx.x == 0 && ptid == 0 && it < 64) g_halo_trace[0][it][1] = clock64();
       img += img_step; j += j_step;
       if (j >= p.tiles_per_img) { j -= p.tiles_per_img; ++img; }
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -263,7 +269,7 @@ igemm_halo_kernel(const HaloParams p) {
     int j = cta % p.tiles_per_img;
     const int j_step = p.ctas_per_nt % p.tiles_per_img;
     mbar_wait(&b_bar, 0);
-    if (p.trace && blockIdx.x == 0 && leader) g_halo_marks[2] = clock64();
+    if (kTrace && p.trace && blockIdx.x == 0 && leader) g_halo_marks[2] = clock64();
     int ti = 0;
     for (int item = cta; item < p.items; item += p.ctas_per_nt, ++ti) {
       const int s0 = p.P + BM * j;
@@ -271,17 +277,17 @@ igemm_halo_kernel(const HaloParams p) {
       const int rel0 = s0 - y0 * p.P;           // tile's first output slot relative to the buffer
       j += j_step;
       if (j >= p.tiles_per_img) j -= p.tiles_per_img;
-      if (p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[2][ti][0] = clock64();
+      if (kTrace && p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[2][ti][0] = clock64();
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      if (p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[2][ti][1] = clock64();
+      if (kTrace && p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[2][ti][1] = clock64();
       mbar_wait(&full_bar[stage], phase);
       fence_proxy_async();     // generic-proxy (cp.async) writes -> visible to the tensor core's async-proxy reads
       tc_fence_after();
-      if (p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[1][ti][0] = clock64();
+      if (kTrace && p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[1][ti][0] = clock64();
       const uint64_t a_desc0 = make_desc_nosw(a_first + (uint32_t)stage * p.a_stage_bytes + (uint32_t)(rel0 * 16), p.a_plane_bytes, 128);
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
       const bool issuer = elect_one();
-      if (issuer && !(p.ablate & 4)) {
+      if (issuer && !(kTrace && (p.ablate & 4))) {
 #pragma unroll
         for (int t = 0; t < T_; ++t) {
           // tap (dy, dx) of the A operand == start address shifted by (dy*P + dx) slots of 16 bytes
@@ -295,12 +301,12 @@ igemm_halo_kernel(const HaloParams p) {
       }
       if (issuer) {
         if (!p.one_commit) tc_commit(&empty_bar[stage]);
-        if (p.trace && blockIdx.x == 0 && ti >= 2 && ti < 5) g_halo_mma_trace[ti - 2][78] = clock64();
+        if (kTrace && p.trace && blockIdx.x == 0 && ti >= 2 && ti < 5) g_halo_mma_trace[ti - 2][78] = clock64();
         tc_commit(&tmem_full[acc]);
-        if (p.trace && blockIdx.x == 0 && ti >= 2 && ti < 5) g_halo_mma_trace[ti - 2][79] = clock64();
+        if (kTrace && p.trace && blockIdx.x == 0 && ti >= 2 && ti < 5) g_halo_mma_trace[ti - 2][79] = clock64();
       }
       __syncwarp();
-      if (p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[1][ti][1] = clock64();
+      if (kTrace && p.trace && blockIdx.x == 0 && leader && ti < 64) g_halo_trace[1][ti][1] = clock64();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
       if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
@@ -309,6 +315,17 @@ igemm_halo_kernel(const HaloParams p) {
     // warps 0-3 take the low half of the tile's channels, warps 8-11 the high half; warp w reads the
     // TMEM lane quarter w % 4 (hardware restriction), i.e. 32 of the tile's 128 output slots.
     const int q = warp & 3, half = warp >> 3;
+    constexpr bool bnb = BNB_;
+    if (bnb) {
+      const int et0 = (warp < 4) ? tid : tid - 128;      // 0..255 over the eight epilogue warps
+      for (int i = et0; i < p.groups * p.BN; i += 256) {
+        const int g = i / p.BN, c = i - g * p.BN;
+        const size_t k = (size_t)g * p.N + nt * p.BN + c;
+        const float rs = rsqrtf(p.bn_var[k] + p.bn_eps);
+        s_coef[g][0][c] = p.bn_scale[k]; s_coef[g][1][c] = p.bn_shift[k]; s_coef[g][2][c] = rs; s_coef[g][3][c] = -p.bn_mean[k] * rs;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     const int nchunk = (p.BN >= 32) ? (p.BN >> 5) : (half == 0 ? 1 : 0);   // 16-column chunks owned by this warp
     const int cbase = half * (p.BN >> 1);                                  // first column of this warp (BN >= 32)
     const bool reg_stats = p.BN <= 64;
@@ -341,6 +358,11 @@ igemm_halo_kernel(const HaloParams p) {
       }
     };
     int ti = 0, estage = 0;
+    // The side operand of the epilogue (residual, or the BatchNorm input of the fused backward statistics) is loaded into
+    // registers before the accumulator wait.  MEASURED alternatives that did not pay (profiles/r02_kernel_findings.md):
+    // prefetch.global.L1 three tiles ahead (no change) and staging it in the tile's shared-memory stage with one bulk copy
+    // per tile (64 -> 70 us for the fused-statistics input gradient): the epilogue is bound by LSU work, not by this latency.
+    const bf16* side = bnb ? p.bn_y : p.res;
     for (int item = cta; item < p.items; item += p.ctas_per_nt, ++ti) {
       const int s = p.P + BM * j + q * 32 + lane;      // this thread's output slot
       const int y = (int)(((uint32_t)s * p.inv_P) >> 16), x = s - y * p.P;   // padded coordinates
@@ -349,130 +371,26 @@ igemm_halo_kernel(const HaloParams p) {
       const uint32_t pix = (uint32_t)((img * p.OHf + oh * p.out_stride + p.out_off_y) * p.OWf + ow * p.out_stride + p.out_off_x);
       const uint32_t obase = pix * (uint32_t)p.N + (uint32_t)(nt * p.BN + cbase);   // element offset (< 2^31 by construction)
       const int g = img / p.group_images;
-      const int img_t = img, jt = j;
       img += img_step; j += j_step;
       if (j >= p.tiles_per_img) { j -= p.tiles_per_img; ++img; }
       if (p.stats != nullptr && g != cur_g) { flush_stats(cur_g); cur_g = g; }
-      if (p.staged) {
-        // ---- staged epilogue: the tile is assembled in shared memory and moved by the bulk-copy engine in
-        // whole image-row segments (W pixels x N channels contiguous in NHWC), so the LSU/L1 path that also
-        // feeds the tensor core's shared-memory operand reads sees no scattered global traffic at all
-        const int b = ti & 1;
-        uint8_t* stg = smem + p.stg_off + (size_t)b * (BM * p.BN * 2);
-        const int s_first = p.P + BM * jt;                 // first slot of the tile
-        const bool elected = (warp == 0 && lane == 0);
-        if (elected) {
-          bulk_wait_read<1>();                             // stores of tile ti-2 have finished reading this buffer
-          if (p.res != nullptr) {
-            // residual: bulk-load the same row segments into the staging buffer
-            uint32_t bytes = 0;
-            for (int y = (int)(((uint32_t)s_first * p.inv_P) >> 16); y <= p.H; ++y) {
-              const int lo = max(s_first, y * p.P + 1), hi = min(s_first + BM, y * p.P + p.W + 1);
-              if (lo >= s_first + BM) break;
-              if (hi > lo) bytes += (uint32_t)(hi - lo) * p.BN * 2;
-            }
-            mbar_expect_tx(&res_bar[b], bytes);
-            for (int y = (int)(((uint32_t)s_first * p.inv_P) >> 16); y <= p.H; ++y) {
-              const int lo = max(s_first, y * p.P + 1), hi = min(s_first + BM, y * p.P + p.W + 1);
-              if (lo >= s_first + BM) break;
-              if (hi > lo) {
-                const size_t gpix = ((size_t)img_t * p.OHf + (y - 1)) * p.OWf + (lo - y * p.P - 1);
-                bulk_load(stg + (size_t)(lo - s_first) * p.BN * 2, p.res + gpix * p.N, (uint32_t)(hi - lo) * p.BN * 2, &res_bar[b]);
-              }
-            }
-          }
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");     // buffer b is free (and residual loads are in flight)
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        if (p.one_commit) { if (warp == 0 && lane == 0) mbar_arrive(&empty_bar[estage]); if (++estage == p.stages) estage = 0; }
-        if (p.res != nullptr) mbar_wait(&res_bar[b], (uint32_t)((ti >> 1) & 1));
-        if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][0] = clock64();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + cbase);
-        uint8_t* srow = stg + (size_t)(q * 32 + lane) * p.BN * 2 + (size_t)cbase * 2;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < nchunk) {
-            const int c0 = k * 16;
-            uint32_t raw[16];
-            tc_ld16(taddr + c0, raw);
-            tc_ld_wait();
-            float v[16];
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(raw[jj]);
-            if (p.bias != nullptr) {
-              const int n0 = nt * p.BN + cbase + c0;
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) v[jj] += p.bias[n0 + jj];
-            }
-            if (row_ok) {
-              if (p.res != nullptr) {
-                float rr[16];
-                unpack8(*reinterpret_cast<const bf16x8*>(srow + c0 * 2), rr);
-                unpack8(*reinterpret_cast<const bf16x8*>(srow + c0 * 2 + 16), rr + 8);
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) v[jj] += rr[jj];
-              }
-              const bf16x8 o0 = pack8(v), o1 = pack8(v + 8);
-              *reinterpret_cast<bf16x8*>(srow + c0 * 2) = o0;
-              *reinterpret_cast<bf16x8*>(srow + c0 * 2 + 16) = o1;
-              if (p.stats != nullptr) { unpack8(o0, v); unpack8(o1, v + 8); }
-            } else {
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
-            }
-            if (p.stats != nullptr) {
-              if (reg_stats) {
-                if (k < 2) {
-#pragma unroll
-                  for (int jj = 0; jj < 16; ++jj) { a1[k][jj] += v[jj]; a2[k][jj] = fmaf(v[jj], v[jj], a2[k][jj]); }
-                }
-              } else {
-                float sq[16];
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) sq[jj] = v[jj] * v[jj];
-                const float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
-                if (lane < 16) {
-                  atomicAdd(&s_stat[g][0][cbase + c0 + lane], s1);
-                  atomicAdd(&s_stat[g][1][cbase + c0 + lane], s2);
-                }
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);       // accumulator is free as soon as it is in registers
-        fence_proxy_async();                               // st.shared -> visible to the bulk-copy (async) proxy
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        if (elected) {
-          for (int y = (int)(((uint32_t)s_first * p.inv_P) >> 16); y <= p.H; ++y) {
-            const int lo = max(s_first, y * p.P + 1), hi = min(s_first + BM, y * p.P + p.W + 1);
-            if (lo >= s_first + BM) break;
-            if (hi > lo) {
-              const size_t gpix = ((size_t)img_t * p.OHf + (y - 1)) * p.OWf + (lo - y * p.P - 1);
-              bulk_store(p.out + gpix * p.N, stg + (size_t)(lo - s_first) * p.BN * 2, (uint32_t)(hi - lo) * p.BN * 2);
-            }
-          }
-          bulk_commit();
-        }
-        if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][1] = clock64();
-        if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
       // residual rows are fetched BEFORE waiting for the accumulator, so their latency is hidden
       bf16x8 rres[8];
-      const bool use_res = p.res != nullptr && row_ok;
-      if (use_res) {
+      const bool use_res = !bnb && p.res != nullptr && row_ok;
+      const bool use_y = bnb && row_ok;                // BatchNorm input at the same pixels (same layout as the output)
+      if ((use_res || use_y) && !(kTrace && (p.ablate & 16))) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (k < nchunk) ld_global_32B(p.res + obase + k * 16, rres[2 * k], rres[2 * k + 1]);
+          if (k < nchunk) ld_global_32B(side + obase + k * 16, rres[2 * k], rres[2 * k + 1]);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      // the tile's MMAs are complete: its A stage can be refilled (saves the MMA warp a second tcgen05.commit)
-      if (p.one_commit) { if (warp == 0 && lane == 0) mbar_arrive(&empty_bar[estage]); if (++estage == p.stages) estage = 0; }
-      if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][0] = clock64();
+      if (p.one_commit) {
+        // the tile's MMAs are complete: its A stage can be refilled (saves the MMA warp a second tcgen05.commit)
+        if (warp == 0 && lane == 0) mbar_arrive(&empty_bar[estage]);
+        if (++estage == p.stages) estage = 0;
+      }
+      if (kTrace && p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][0] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + cbase);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -489,7 +407,7 @@ igemm_halo_kernel(const HaloParams p) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) v[jj] += p.bias[n0 + jj];
           }
-          if (row_ok && !(p.ablate & 2)) {
+          if (row_ok && !(kTrace && (p.ablate & 2))) {
             if (use_res) {
               float rr[16];
               unpack8(rres[2 * k], rr);
@@ -505,15 +423,35 @@ igemm_halo_kernel(const HaloParams p) {
             for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
           }
           if (p.stats != nullptr) {
+            float sq[16];
+            if (bnb) {
+              // v = stored output gradient w.r.t. the activated tensor -> dz (through the activation) and dz * x_hat
+              if (use_y && !(kTrace && (p.ablate & 8))) {
+                float yv[16];
+                unpack8(rres[2 * k], yv);
+                unpack8(rres[2 * k + 1], yv + 8);
+                const float4* cf = reinterpret_cast<const float4*>(&s_coef[g][0][cbase + c0]);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+                  bn_bwd_terms4(yv + 4 * j4, cf[j4], cf[32 + j4], cf[64 + j4], cf[96 + j4], p.bn_slope, v + 4 * j4, sq + 4 * j4);
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) sq[jj] = 0.f;
+              }
+            }
             if (reg_stats) {
               if (k < 2) {
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) { a1[k][jj] += v[jj]; a2[k][jj] = fmaf(v[jj], v[jj], a2[k][jj]); }
+                for (int jj = 0; jj < 16; ++jj) {
+                  a1[k][jj] += v[jj];
+                  a2[k][jj] = bnb ? a2[k][jj] + sq[jj] : fmaf(v[jj], v[jj], a2[k][jj]);
+                }
               }
             } else {
-              float sq[16];
+              if (!bnb) {
 #pragma unroll
-              for (int jj = 0; jj < 16; ++jj) sq[jj] = v[jj] * v[jj];
+                for (int jj = 0; jj < 16; ++jj) sq[jj] = v[jj] * v[jj];
+              }
               const float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
               if (lane < 16) {
                 atomicAdd(&s_stat[g][0][cbase + c0 + lane], s1);
@@ -526,10 +464,9 @@ igemm_halo_kernel(const HaloParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][1] = clock64();
+      if (kTrace && p.trace && blockIdx.x == 0 && tid == 0 && ti < 64) g_halo_trace[3][ti][1] = clock64();
       if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.staged && warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (p.stats != nullptr) {
       flush_stats(cur_g);
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -538,14 +475,16 @@ igemm_halo_kernel(const HaloParams p) {
         const int g = i / (2 * p.BN), rem = i - g * 2 * p.BN;
         const int st = rem / p.BN, c = rem - st * p.BN;
         const float val = s_stat[g][st][c];
-        if (val != 0.f) atomicAdd(&p.stats[(size_t)(g * 2 + st) * p.N + nt * p.BN + c], val);
+        // forward statistics are [G][2][N]; the BatchNorm-backward pair is [2][G][N] (dbeta block, then dgamma block)
+        const size_t slot = BNB_ ? (size_t)(st * p.groups + g) : (size_t)(g * 2 + st);
+        if (val != 0.f) atomicAdd(&p.stats[slot * p.N + nt * p.BN + c], val);
       }
     }
   }
   tc_fence_before();
-  if (p.trace && blockIdx.x == 0 && tid == 0) g_halo_marks[3] = clock64();
+  if (kTrace && p.trace && blockIdx.x == 0 && tid == 0) g_halo_marks[3] = clock64();
   __syncthreads();
-  if (p.trace && blockIdx.x == 0 && tid == 0) g_halo_marks[4] = clock64();
+  if (kTrace && p.trace && blockIdx.x == 0 && tid == 0) g_halo_marks[4] = clock64();
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -580,6 +519,7 @@ bool igemm_fprop_halo_supported(const IgemmParams& p) {
   for (int t = 0; t < p.T; ++t)
     if (p.dy[t] < -1 || p.dy[t] > 1 || p.dx[t] < -1 || p.dx[t] > 1) return false;
   if (p.stats != nullptr && p.NB / p.group_images > MAX_GROUPS) return false;
+  if (p.bn_y != nullptr && (p.out_stride != 1 || p.OHf != p.OH || p.OWf != p.OW || (reinterpret_cast<uintptr_t>(p.bn_y) & 31))) return false;
   if (pick_bn(p) == 0) return false;
   if (!(p.T == 1 || p.T == 2 || p.T == 4 || p.T == 9)) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.Wt) & 15)) return false;
@@ -613,17 +553,7 @@ int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st) {
   q.b_tap_bytes = (uint32_t)(p.C / 8) * q.b_plane_bytes;
   q.b_bytes = (uint32_t)p.T * q.b_tap_bytes;
   const size_t b_alloc = (q.b_bytes + 1023) & ~(size_t)1023;
-  // staged epilogue: needs contiguous output rows (whole channel range in this CTA, unit output stride)
-  // MEASURED (round 1): correct but ~35 % slower than the direct stores (one elected thread, two 256-thread
-  // barriers and the bulk-copy latency per tile), so it is off unless SHOTVAE_HALO_STAGE=1 (kept for round 2)
-  q.staged = 0;
-  {
-    static int stage_on = -1;
-    if (stage_on < 0) { const char* e = getenv("SHOTVAE_HALO_STAGE"); stage_on = (e && e[0] == '1') ? 1 : 0; }
-    if (stage_on && q.n_tiles == 1 && p.out_stride == 1 && p.OHf == p.H && p.OWf == p.W) q.staged = 1;
-  }
-  const size_t stg_bytes = q.staged ? (size_t)2 * BM * q.BN * 2 : 0;
-  int stages = (int)((196 * 1024 - b_alloc - stg_bytes) / q.a_stage_bytes);
+  int stages = (int)((196 * 1024 - b_alloc) / q.a_stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { sv_set_error("igemm_halo: tile does not fit"); return SV_ERR_UNSUPPORTED; }
   q.stages = stages;
@@ -648,6 +578,8 @@ int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st) {
 
   q.A = p.A;
   q.Wp = p.Wt;
+  q.bn_y = p.bn_y; q.bn_scale = p.bn_scale; q.bn_shift = p.bn_shift; q.bn_mean = p.bn_mean; q.bn_var = p.bn_var;
+  q.bn_slope = p.bn_slope; q.bn_eps = p.bn_eps;
   q.planes = p.C / 8;
   q.planes_log2 = 0;
   while ((1 << q.planes_log2) < q.planes) ++q.planes_log2;
@@ -661,24 +593,28 @@ int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st) {
     if (ablate < 0) { const char* e = getenv("SHOTVAE_HALO_ABLATE"); ablate = e ? atoi(e) : 0; }
     q.ablate = ablate;
   }
-  q.stg_off = (uint32_t)(b_alloc + (size_t)stages * q.a_stage_bytes);
-  const size_t smem = b_alloc + (size_t)stages * q.a_stage_bytes + stg_bytes + 1024;
+  const size_t smem = b_alloc + (size_t)stages * q.a_stage_bytes + 1024;
   const int grid = q.ctas_per_nt * q.n_tiles;
   const int kc = p.C / 16;
-#define SV_HALO_CASE(TT, KK)                                                                                   \
-  if (p.T == TT && kc == KK) {                                                                                 \
-    static bool configured = false;                                                                            \
-    if (!configured) {                                                                                         \
-      cudaFuncSetAttribute(igemm_halo_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-      configured = true;                                                                                       \
-    }                                                                                                          \
-    sv_launch_pdl(igemm_halo_kernel<TT, KK>, dim3(grid), dim3(HL_THREADS), smem, st, q);                                              \
-    return sv_check_launch("igemm_halo");                                                                      \
+#define SV_HALO_LAUNCH(TT, KK, BB)                                                                                   \
+  {                                                                                                                 \
+    static bool configured = false;                                                                                 \
+    if (!configured) {                                                                                              \
+      cudaFuncSetAttribute(igemm_halo_kernel<TT, KK, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
+      configured = true;                                                                                            \
+    }                                                                                                               \
+    sv_launch_pdl(igemm_halo_kernel<TT, KK, BB>, dim3(grid), dim3(HL_THREADS), smem, st, q);                         \
+    return sv_check_launch("igemm_halo");                                                                           \
+  }
+#define SV_HALO_CASE(TT, KK)                                                                                         \
+  if (p.T == TT && kc == KK) {                                                                                       \
+    if (p.bn_y != nullptr) SV_HALO_LAUNCH(TT, KK, true) else SV_HALO_LAUNCH(TT, KK, false)                            \
   }
 #define SV_HALO_TAPS(TT) SV_HALO_CASE(TT, 1) SV_HALO_CASE(TT, 2) SV_HALO_CASE(TT, 4) SV_HALO_CASE(TT, 8)
   SV_HALO_TAPS(1) SV_HALO_TAPS(2) SV_HALO_TAPS(4) SV_HALO_TAPS(9)
 #undef SV_HALO_TAPS
 #undef SV_HALO_CASE
+#undef SV_HALO_LAUNCH
   sv_set_error("igemm_halo: no instantiation for T=%d, C=%d", p.T, p.C);
   return SV_ERR_UNSUPPORTED;
 }

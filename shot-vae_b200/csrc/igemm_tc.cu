@@ -47,6 +47,13 @@ struct TcParams {
   int swizzle_bytes;         // 64 or 128
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
+  // fused BatchNorm-backward statistics (input-gradient launches, see sv_igemm_args)
+  const bf16* bn_y;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_var;
+  float bn_slope, bn_eps;
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -132,6 +139,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
   __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_stat[MAX_GROUPS][2][256];
+  __shared__ __align__(16) float s_coef[MAX_GROUPS][4][256];     // {scale, shift, rstd, -mean*rstd} of the current channel tile
 
   pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31;
@@ -235,8 +243,22 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     const int ohw = p.OH * p.OW;
+    const bool bnb = p.bn_y != nullptr;
+    int coef_nt = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      if (bnb && nt != coef_nt) {
+        // coefficients of this channel tile for every pass group (a CTA's tiles mostly share nt: refilled on change only)
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int i = tid - 128; i < p.groups * p.BN; i += 128) {
+          const int g = i / p.BN, c = i - g * p.BN;
+          const size_t k = (size_t)g * p.N + nt * p.BN + c;
+          const float rs = rsqrtf(p.bn_var[k] + p.bn_eps);
+          s_coef[g][0][c] = p.bn_scale[k]; s_coef[g][1][c] = p.bn_shift[k]; s_coef[g][2][c] = rs; s_coef[g][3][c] = -p.bn_mean[k] * rs;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        coef_nt = nt;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = mt * BM + q * 32 + lane;
@@ -251,7 +273,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
         uint32_t raw[16];
         tc_ld16(taddr + c0, raw);
         tc_ld_wait();
-        float v[16];
+        float v[16], sq[16];
         const int n0 = nt * p.BN + c0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
@@ -273,15 +295,27 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
           st_global_32B(p.out + pix * p.N + n0, o0, o1);
           unpack8(o0, v);
           unpack8(o1, v + 8);
+          if (bnb) {
+            float yv[16];
+            bf16x8 y0, y1;
+            ld_global_32B(p.bn_y + pix * p.N + n0, y0, y1);
+            unpack8(y0, yv);
+            unpack8(y1, yv + 8);
+            const float4* cf = reinterpret_cast<const float4*>(&s_coef[g][0][c0]);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              bn_bwd_terms4(yv + 4 * j4, cf[j4], cf[64 + j4], cf[128 + j4], cf[192 + j4], p.bn_slope, v + 4 * j4, sq + 4 * j4);
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          for (int j = 0; j < 16; ++j) { v[j] = 0.f; sq[j] = 0.f; }
         }
         if (p.stats != nullptr) {
           // 16 columns x 32 rows -> per-column sums by a butterfly transpose-reduce (20 shuffles instead of 160)
-          float sq[16];
+          if (!bnb) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+            for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+          }
           const float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
           if (lane < 16) {
             atomicAdd(&s_stat[g][0][c0 + lane], s1);
@@ -300,7 +334,8 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
         for (int i = et; i < 2 * p.BN; i += 128) {
           const int s = i / p.BN, c = i - s * p.BN;
           const float val = s_stat[g][s][c];
-          if (val != 0.f) atomicAdd(&p.stats[(size_t)(g * 2 + s) * p.N + nt * p.BN + c], val);
+          const size_t slot = bnb ? (size_t)(s * p.groups + g) : (size_t)(g * 2 + s);     // BatchNorm-backward pair: [2][G][N]
+          if (val != 0.f) atomicAdd(&p.stats[slot * p.N + nt * p.BN + c], val);
           s_stat[g][s][c] = 0.f;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -313,7 +348,8 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
         const int g = i / (2 * p.BN), rem = i - g * 2 * p.BN;
         const int s = rem / p.BN, c = rem - s * p.BN;
         const float val = s_stat[g][s][c];
-        if (val != 0.f) atomicAdd(&p.stats[(size_t)(g * 2 + s) * p.N + c], val);
+        const size_t slot = bnb ? (size_t)(s * p.groups + g) : (size_t)(g * 2 + s);
+        if (val != 0.f) atomicAdd(&p.stats[slot * p.N + c], val);
       }
     }
   }
@@ -413,6 +449,7 @@ bool igemm_fprop_tc_supported(const IgemmParams& p) {
   if (pick_bn(p.N) == 0) return false;
   if (p.out == nullptr || p.outf != nullptr) return false;
   if (p.stats != nullptr && (p.rows_per_group % BM != 0 || p.NB / p.group_images > MAX_GROUPS)) return false;
+  if (p.bn_y != nullptr && (p.stats == nullptr || (reinterpret_cast<uintptr_t>(p.bn_y) & 31))) return false;
   if (p.NB < g.Nt) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.Wt) & 15)) return false;
   if ((reinterpret_cast<uintptr_t>(p.out) & 31) || (reinterpret_cast<uintptr_t>(p.res) & 31)) return false;   // 32-byte epilogue accesses
@@ -443,6 +480,8 @@ static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtenso
   q.n_tiles = p.N / bn;
   q.rows_per_group = p.rows_per_group;
   q.groups = p.NB / p.group_images;
+  q.bn_y = p.bn_y; q.bn_scale = p.bn_scale; q.bn_shift = p.bn_shift; q.bn_mean = p.bn_mean; q.bn_var = p.bn_var;
+  q.bn_slope = p.bn_slope; q.bn_eps = p.bn_eps;
   q.swizzle_bytes = q.KB * 2;
   const size_t stage_bytes = ((size_t)BM * q.KB * 2 + (size_t)q.BN * q.KB * 2 + 1023) & ~(size_t)1023;
   int stages = (int)((192 * 1024) / stage_bytes);

@@ -27,7 +27,8 @@ class IgemmArgs(C.Structure):
                 ("NB", i32), ("H", i32), ("W", i32), ("C", i32), ("OH", i32), ("OW", i32), ("N", i32), ("T", i32),
                 ("in_stride", i32), ("out_stride", i32), ("out_off_y", i32), ("out_off_x", i32),
                 ("OHf", i32), ("OWf", i32), ("n_valid", i32), ("group_images", i32),
-                ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS), ("impl", i32), ("w_layout", i32)]
+                ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS), ("impl", i32), ("w_layout", i32),
+                ("bn_y", vp), ("bn_scale", vp), ("bn_shift", vp), ("bn_mean", vp), ("bn_var", vp), ("bn_slope", f32), ("bn_eps", f32)]
 
 
 class WgradArgs(C.Structure):

@@ -24,6 +24,8 @@ from ._abi import lib, check, ptr, IgemmArgs, WgradArgs, BnBwdTerm, taps_array
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+# SHOTVAE_FUSE_BNBWD=0: BatchNorm-backward statistics by the separate sv_bn_bwd_reduce pass everywhere (A/B switch)
+FUSE_BN_BWD = os.environ.get("SHOTVAE_FUSE_BNBWD", "1") != "0"
 WG_WORKSPACE_FLOATS = 24 * 1024 * 1024
 
 
@@ -317,9 +319,13 @@ class Net:
 
     # ---- low-level launch helpers --------------------------------------------------------------
     def _igemm(self, ctx, key, A, pack, NB, H, W, OH, OW, in_stride=1, out=None, outf=None, res=None, bias=None, stats=None,
-               out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0, exact=False, batch=None):
+               out_stride=1, off=(0, 0), OHf=None, OWf=None, n_valid=0, exact=False, batch=None, bnb=None):
         """batch: a list -> the launch is deferred; _igemm_flush(batch) issues all of them through sv_igemm_fprop_batch
-        (independent problems, e.g. the four output-parity phases of a transposed convolution)"""
+        (independent problems, e.g. the four output-parity phases of a transposed convolution).
+        bnb = dict(rec, y, slope): input-gradient launch whose epilogue also accumulates the BatchNorm-backward statistics of
+        BatchNorm `rec` (input y) into `stats` ([2][G][N]: dbeta block, dgamma block); returns False (nothing launched, nothing
+        changed) when the kernel that runs this shape has no such epilogue, so that the caller can fall back to
+        sv_bn_bwd_reduce."""
         a = ctx.args.get(key)
         if a is None:
             pk = self.packs[pack]
@@ -338,14 +344,26 @@ class Net:
         # operand pointers are refreshed on every call (callers may hand in different tensors)
         a.A, a.out_bf16, a.out_f32, a.residual, a.bias, a.stats = ptr(A), ptr(out), ptr(outf), ptr(res), ptr(bias), ptr(stats)
         a.impl = 3 if a.w_layout == 1 else (self.impl if self.impl != 3 else 0)
+        if bnb is not None:
+            rec = bnb["rec"]
+            a.bn_y, a.bn_scale, a.bn_shift, a.bn_mean, a.bn_var = ptr(bnb["y"]), ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"])
+            a.bn_slope, a.bn_eps = float(bnb["slope"]), BN_EPS
+            ok = ctx.args.get(key + "#bnb")
+            if ok is None:
+                ok = ctx.args[key + "#bnb"] = bool(FUSE_BN_BWD and lib.sv_igemm_fprop_supports(C.byref(a), a.impl))
+            if not ok:
+                a.bn_y = None
+                return False
+        else:
+            a.bn_y = None
         if self.dry:
-            return
+            return True
         if batch is not None and self.timing is None:
             batch.append(a)
-            return
+            return True
         if self.timing is None:
             check(lib.sv_igemm_fprop(C.byref(a), _abi.stream()))
-            return
+            return True
         pk = self.packs[pack]
         flops = 2.0 * pk["n_real"] * pk["c_real"] * _valid_pairs(pk["taps"], NB, OH, OW, H, W, in_stride, exact)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -356,6 +374,7 @@ class Net:
         nbytes = esz(A) // (in_stride * in_stride) + esz(pk["w"]) + esz(res) + NB * OH * OW * pk["N"] * ((2 if out is not None else 0) +
                                                                                                   (4 if outf is not None else 0))
         self.timing.append(("igemm_fprop", key, flops, e0, e1, nbytes))
+        return True
 
     def _igemm_flush(self, batch):
         if not batch:
@@ -468,6 +487,12 @@ class Net:
         check(lib.sv_bn_act_fwd(ptr(y), ptr(a), ptr(rec["scale"]), ptr(rec["shift"]), float(slope), rows_per_group, ctx.G,
                                 rec["C"], _abi.stream()))
 
+    def _bn_bwd_stats(self, ctx, key, i, Cc):
+        """(dbeta, dgamma) accumulators [G][C] of term i of BatchNorm `key`: one zero-arena buffer [2][G][C], the layout the
+        fused input-gradient epilogue writes"""
+        st = ctx.z("%s.bst%d" % (key, i), 2 * ctx.G * Cc)
+        return st[:ctx.G * Cc], st[ctx.G * Cc:]
+
     def _bn_bwd(self, ctx, key, terms, y, addend, g_y, rows_per_group, HW):
         """terms: list of dict(rec, g_a | g_feat, slope).  Runs the dgamma/dbeta reductions and the apply."""
         G = ctx.G
@@ -476,11 +501,12 @@ class Net:
         s = _abi.stream()
         for i, t in enumerate(terms):
             rec = t["rec"]
-            dg, db = ctx.z("%s.dg%d" % (key, i), G * Cc), ctx.z("%s.db%d" % (key, i), G * Cc)
+            db, dg = self._bn_bwd_stats(ctx, key, i, Cc)
             gb = 2 * t["g_a"].numel() if t.get("g_a") is not None else 0
-            self._timed("bn_bwd_reduce", key, gb + 2 * y.numel(), lambda: check(lib.sv_bn_bwd_reduce(
-                ptr(t.get("g_a")), ptr(t.get("g_feat")), ptr(y), ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"]),
-                BN_EPS, float(t["slope"]), rows_per_group, HW, G, Cc, ptr(dg), ptr(db), s)))
+            if not t.get("fused"):           # (fused: the input-gradient conv's epilogue has already accumulated db / dg)
+                self._timed("bn_bwd_reduce", key, gb + 2 * y.numel(), lambda: check(lib.sv_bn_bwd_reduce(
+                    ptr(t.get("g_a")), ptr(t.get("g_feat")), ptr(y), ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"]),
+                    BN_EPS, float(t["slope"]), rows_per_group, HW, G, Cc, ptr(dg), ptr(db), s)))
             arr[i].g_a, arr[i].g_feat = ptr(t.get("g_a")), ptr(t.get("g_feat"))
             arr[i].scale, arr[i].shift, arr[i].mean, arr[i].var = ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"])
             arr[i].dgamma, arr[i].dbeta = ptr(dg), ptr(db)
@@ -585,13 +611,16 @@ class Net:
             # conv2: input gradient (main), weight gradient (side)
             ev = ready()
             g_a2 = ctx.t("g.a2.%d.%d" % (Ho, u.cout), (NB, Ho, Ho, u.cout))
-            self._igemm(ctx, k + ".conv2.d", g_out, k + ".conv2.d00", NB, Ho, Ho, Ho, Ho, out=g_a2)
+            f2 = self._igemm(ctx, k + ".conv2.d", g_out, k + ".conv2.d00", NB, Ho, Ho, Ho, Ho, out=g_a2,
+                             stats=ctx.z(k + ".bn2.bst0", 2 * G * u.cout), bnb=dict(rec=rec["bn2"], y=rec["y1"], slope=slope))
+            if not f2:
+                self._igemm(ctx, k + ".conv2.d", g_out, k + ".conv2.d00", NB, Ho, Ho, Ho, Ho, out=g_a2)
             on_side(lambda: self._wgrad(ctx, k + ".conv2.w", rec["a2"], g_out, conv_taps(3, 1), NB, Ho, Ho, u.cout, Ho, Ho, u.cout, 1,
                                         u.prefix + ".f_block.conv2.weight", u.cout, u.cout, u.cout * K9, K9, 1), ev)
             g_y1 = ctx.t("g.y1.%d.%d" % (Ho, u.cout), (NB, Ho, Ho, u.cout))
             if side_done is not None:
                 main.wait_event(side_done)      # the previous unit's conv1 weight gradient has read g.y1 / its g_out
-            self._bn_bwd(ctx, k + ".bn2", [dict(rec=rec["bn2"], g_a=g_a2, slope=slope)], rec["y1"], None, g_y1, rows_out, Ho * Ho)
+            self._bn_bwd(ctx, k + ".bn2", [dict(rec=rec["bn2"], g_a=g_a2, slope=slope, fused=f2)], rec["y1"], None, g_y1, rows_out, Ho * Ho)
 
             # conv1 (+ projection shortcut)
             def wgrads1():
@@ -602,15 +631,17 @@ class Net:
                                 u.prefix + ".i_block.conv.weight", u.cout, u.cin, u.cin, 1, 1)
             ev = ready()
             g_a1 = ctx.t("g.a1.%d.%d" % (Hin, u.cin), (NB, Hin, Hin, u.cin))
-            self._dgrad(ctx, k + ".conv1", g_y1, g_a1, NB, Ho, Hin, u.stride)
+            f1 = self._dgrad(ctx, k + ".conv1", g_y1, g_a1, NB, Ho, Hin, u.stride,
+                             bnb=dict(rec=rec["bn1"], y=rec["h_in"], slope=slope, stats=ctx.z(k + ".bn1.bst0", 2 * G * u.cin)))
             on_side(wgrads1, ev)
             side_done = mark_side()
-            terms = [dict(rec=rec["bn1"], g_a=g_a1, slope=slope)]
+            terms = [dict(rec=rec["bn1"], g_a=g_a1, slope=slope, fused=f1)]
             addend = g_out
             if u.shortcut:
                 g_as = ctx.t("g.as.%d.%d" % (Hin, u.cin), (NB, Hin, Hin, u.cin))
-                self._dgrad(ctx, k + ".sc", g_out, g_as, NB, Ho, Hin, u.stride)
-                terms.append(dict(rec=rec["bns"], g_a=g_as, slope=sslope))
+                fs = self._dgrad(ctx, k + ".sc", g_out, g_as, NB, Ho, Hin, u.stride,
+                                 bnb=dict(rec=rec["bns"], y=rec["h_in"], slope=sslope, stats=ctx.z(k + ".bn1.bst1", 2 * G * u.cin)))
+                terms.append(dict(rec=rec["bns"], g_a=g_as, slope=sslope, fused=fs))
                 addend = None
             flip ^= 1
             g_prev = ctx.t("g.h.%d.%d.%d" % (Hin, u.cin, flip), (NB, Hin, Hin, u.cin))
@@ -626,15 +657,22 @@ class Net:
         check(lib.sv_colsum_bf16(ptr(g_h), ptr(self.g("feature_extractor.encoder.pre_process.conv0.bias")), NB * 32 * 32, f0, f0,
                                  _abi.stream()))
 
-    def _dgrad(self, ctx, key, g_out, g_in, NB, Ho, Hin, stride):
-        """input gradient of a conv by output-parity phases (stride 1: a single phase)"""
+    def _dgrad(self, ctx, key, g_out, g_in, NB, Ho, Hin, stride, bnb=None):
+        """input gradient of a conv by output-parity phases (stride 1: a single phase).  bnb (stride 1 only): fuse the
+        BatchNorm-backward statistics of the BatchNorm in front of this conv into the launch; returns whether that happened."""
         s = stride
         phases = [(py, px) for py in range(s) for px in range(s) if ("%s.d%d%d" % (key, py, px)) in self.packs]
+        if s == 1 and bnb is not None and len(phases) == 1:
+            k0 = "%s.d00" % key
+            if self._igemm(ctx, k0, g_out, k0, NB, Ho, Ho, Ho, Ho, out=g_in, OHf=Hin, OWf=Hin, stats=bnb["stats"], bnb=bnb):
+                return True
         if len(phases) < s * s:
             g_in.zero_()
+        fused = False
         for py, px in phases:
             self._igemm(ctx, "%s.d%d%d" % (key, py, px), g_out, "%s.d%d%d" % (key, py, px), NB, Ho, Ho, Ho, Ho, out=g_in,
                         out_stride=s, off=(py, px), OHf=Hin, OWf=Hin)
+        return fused
 
     # ---- heads + sample ------------------------------------------------------------------------
     HEADS = (("continuous_inference.mean", "mu"), ("continuous_inference.log_sigma", "ls"), ("disc_latent_inference", "logits"))

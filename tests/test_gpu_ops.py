@@ -229,6 +229,52 @@ def test_conv_dgrad_phases_match_autograd(sv, impl, cin, cout, H, stride, k, NB)
     assert rel_rms(from_nhwc(gin), x.grad) < 4e-3
 
 
+@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("cin,cout,H,k,NB,G,slope", [(32, 32, 32, 3, 64, 2, 0.01), (64, 64, 16, 3, 128, 4, 0.01), (128, 128, 8, 3, 256, 4, 0.0),
+                                                     (32, 16, 32, 1, 40, 1, 1.0), (32, 32, 32, 3, 512, 4, 0.01), (160, 160, 8, 3, 16, 2, 0.01)])
+def test_dgrad_epilogue_accumulates_bn_backward_statistics(sv, impl, cin, cout, H, k, NB, G, slope):
+    """input-gradient conv with the fused BatchNorm-backward statistics epilogue == the same conv followed by
+    sv_bn_bwd_reduce on its (bf16) output; (cin -> cout is the FORWARD conv: the launch maps cout gradients to cin)"""
+    from shotvae_b200._abi import lib, check, ptr, taps_array, IgemmArgs
+    from shotvae_b200.plan import dgrad_phase_taps
+    torch.manual_seed(cin + cout + H + NB)
+    w = bf(torch.randn(cout, cin, k, k) * 0.1)
+    g_out = nhwc(bf(torch.randn(NB, cout, H, H)))
+    y = nhwc(bf(torch.randn(NB, cin, H, H) * 1.5 + 0.3))
+    scale, shift = (torch.rand(G, cin) + 0.5).cuda(), (torch.randn(G, cin) * 0.3).cuda()
+    mean, var = (torch.randn(G, cin) * 0.2 + 0.3).cuda(), (torch.rand(G, cin) + 0.5).cuda()
+    taps = dgrad_phase_taps(k, 1, k // 2)[(0, 0)]
+    Wt = pack(sv, w, cin, cout, taps, cin, cout, k * k, cin * k * k, 1, impl)
+    a = IgemmArgs()
+    out = torch.empty(NB, H, H, cin, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(2, G, cin, device="cuda")
+    a.A, a.Wt, a.out_bf16, a.stats = ptr(g_out), ptr(Wt), ptr(out), ptr(stats)
+    a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = NB, H, H, cout, H, H, cin, len(taps)
+    a.in_stride, a.out_stride, a.OHf, a.OWf, a.group_images = 1, 1, H, H, NB // G
+    a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
+    a.impl, a.w_layout = impl, (1 if impl == 3 else 0)
+    a.bn_y, a.bn_scale, a.bn_shift, a.bn_mean, a.bn_var, a.bn_slope, a.bn_eps = ptr(y), ptr(scale), ptr(shift), ptr(mean), ptr(var), slope, 1e-5
+    if not lib.sv_igemm_fprop_supports(C.byref(a), impl):
+        pytest.skip("shape not covered by tcgen05 kernel %d" % impl)
+    check(lib.sv_igemm_fprop(C.byref(a), sv.stream()))
+    # reference: plain launch + the separate reduction pass over its output
+    out2 = torch.empty_like(out)
+    a.bn_y, a.stats, a.out_bf16 = None, None, ptr(out2)
+    check(lib.sv_igemm_fprop(C.byref(a), sv.stream()))
+    assert torch.equal(out, out2)
+    dg, db = torch.zeros(G, cin, device="cuda"), torch.zeros(G, cin, device="cuda")
+    check(lib.sv_bn_bwd_reduce(ptr(out2), None, ptr(y), ptr(scale), ptr(shift), ptr(mean), ptr(var), 1e-5, slope, (NB // G) * H * H, H * H, G, cin,
+                               ptr(dg), ptr(db), sv.stream()))
+    assert rel_rms(stats[0], db) < 1e-4 and rel_rms(stats[1], dg) < 1e-4
+    # and against torch on the same bf16 values
+    go = out2.float().view(G, -1, cin)
+    yy = y.float().view(G, -1, cin)
+    pre = yy * scale[:, None] + shift[:, None]
+    dz = torch.where(pre > 0, go, go * slope)
+    xh = (yy - mean[:, None]) * torch.rsqrt(var[:, None] + 1e-5)
+    assert rel_rms(stats[0], dz.sum(1)) < 1e-3 and rel_rms(stats[1], (dz * xh).sum(1)) < 1e-3
+
+
 def wgrad(sv, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, grad, n_real, c_real, sn, sc, st, splits, impl=1):
     from shotvae_b200._abi import lib, check, ptr, taps_array, WgradArgs
     T = len(taps)
