@@ -75,6 +75,8 @@ class TrainStep:
         self.coef = z(16)
         self.sgd_hyper = z(8)
         self.terms = z(16)
+        self.kl_sum = z(1)           # sum of the per-step inference-KL monitor since it was last cleared (Train/KL_Inference, :331-339,376)
+        self.kl_count = 0
         # mixup targets
         self.s_mu, self.s_sig, self.s_alpha = z(B, D), z(B, D), z(B, nd)
         self.m_mu, self.m_sig, self.m_alpha = z(B, D), z(B, D), z(B, nd)
@@ -303,6 +305,7 @@ class TrainStep:
         net, A, Bc, st = self.net, self.ctxA, self.ctxB, _abi.stream()
         # ---- optimizer + BatchNorm running statistics
         check(lib.sv_sgd_step(ptr(net.params), ptr(net.grads), ptr(net.momentum), ptr(self.sgd_hyper), net.n_params, st))
+        self.kl_sum.add_(self.terms[10:11])      # device-side accumulator: the epoch average needs no per-step host sync
         if self.m2:
             net.bn_running_update([(A, 0), (A, 1)])
         else:
@@ -346,6 +349,7 @@ class TrainStep:
             self.launches_per_step = _abi.launch_count() - n0
         self._steps_done += 1
         self._calls += 1
+        self.kl_count += 1
         self.net.param_epoch += 1             # the fused SGD moved the FP32 masters: the drop-in forward must repack
 
     def _replay(self):

@@ -277,3 +277,74 @@ def test_fused_optimizer_state_roundtrip_and_resume():
     o, n, shp = md._net.poff[k0]
     assert torch.equal(md._net.momentum[o:o + n].view(shp), opt.state_dict()["state"][list(dict(md.named_parameters())).index(k0)]["momentum_buffer"])
     assert float(td.sgd_hyper[4]) == 0.0
+
+
+def _loaders(nd, sizes_u, sizes_l, seed):
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda b: (torch.rand(b, 3, 32, 32, generator=g), torch.randint(0, nd, (b,), generator=g))
+    return [mk(b) for b in sizes_u], [mk(b) for b in sizes_l]
+
+
+def test_trainer_epoch_tail_batches_checkpoint_and_resume():
+    """Epoch driver (reference main() / train(), main_shot_vae.py:202-258,261-383): zip(cycle(labelled), unlabelled) with a
+    short unlabelled tail (B_l != B_u -> the autograd path), a second TrainStep for an equal-sized tail, the epoch's
+    KL_Inference average, learning-rate warm-up, and a checkpoint in the reference's dict format that resumes to the
+    same parameters as the uninterrupted run."""
+    import argparse
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.train import Trainer
+    net, nd, B = "wideresnet-10-1", 10, 16
+    hyper = O.default_hyper("Cifar10")
+    st = O.init_state(net, nd)
+    # unlabelled: 16, 16, 16, 8 ; labelled: 16, 8 -> pairs (16,16) (8,16 -> ragged) (16,16) (8,8 -> second engine)
+    lu, ll = _loaders(nd, [16, 16, 16, 8], [16, 8], 5)
+
+    def run(epochs, ckpt_after=None, resume_from=None, rng=None):
+        model = build_model(net, nd, st if resume_from is None else resume_from["state_dict"]).train()
+        tr = Trainer(model, B, hyper=hyper, dataset="Cifar10", adjust_lr=(1, 2, 3), use_graph=False, device_noise=False)
+        if resume_from is not None:
+            tr.load_checkpoint(resume_from)
+        if rng is not None:
+            torch.set_rng_state(rng[0]); np.random.set_state(rng[1])
+        out, ck, snap = [], None, None
+        for epoch in range(tr.start_epoch, epochs):
+            out.append(tr.train_epoch(lu, ll, epoch))
+            if ckpt_after is not None and epoch == ckpt_after:
+                ck, snap = tr.checkpoint(epoch), (torch.get_rng_state(), np.random.get_state())
+        return model, tr, out, ck, snap
+
+    torch.manual_seed(3); np.random.seed(3)
+    ma, ta, ra, ck, snap = run(3, ckpt_after=0)
+    assert [r["steps"] for r in ra] == [4, 4, 4] and [r["ragged_steps"] for r in ra] == [1, 1, 1] and ra[0]["images"] == 56
+    assert sorted(ta.steps) == [8, 16]                                  # one engine per equal batch size
+    assert all(4.0 < r["kl_inference"] < 9.0 for r in ra), ra           # ~ -log(1/nd) + smoothing terms at initialisation
+    assert ta.lr_at(0) == pytest.approx(0.02) and ta.lr_at(1) == pytest.approx(0.1) and ta.lr_at(3) == pytest.approx(0.001)
+    assert float(ta.steps[16].sgd_hyper[0]) == pytest.approx(ta.lr_at(2))
+    # the checkpoint is the reference's dict; its optimizer entry loads into torch.optim.SGD
+    assert set(ck) == {"epoch", "args", "state_dict", "optimizer"} and ck["epoch"] == 1
+    probe = torch.optim.SGD(build_model(net, nd, st).parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    probe.load_state_dict({k: v for k, v in ck["optimizer"].items() if k != "shotvae"})
+    # resume == uninterrupted (same host RNG state at the resume point; only atomics' summation order differs)
+    mb, tb, rb, _, _ = run(3, resume_from=ck, rng=snap)
+    assert tb.start_epoch == 1 and len(rb) == 2
+    sa, sb = ma.state_dict(), mb.state_dict()
+    keys = [k for k in sa if sa[k].dtype == torch.float32 and "running" not in k]
+    errs = grad_errors({k: sb[k].float() for k in keys}, {k: sa[k].float() for k in keys})
+    assert errs["all"] < 1e-2, errs
+    for a, b in zip(ra[1:], rb):
+        assert abs(a["kl_inference"] - b["kl_inference"]) < 2e-2 * abs(a["kl_inference"])
+    # ... and the training moved the parameters at all (ragged steps included)
+    moved = grad_errors({k: sa[k].float().cpu() for k in keys}, {k: st[k].float() for k in keys})
+    assert moved["all"] > 10 * errs["all"]
+    # a checkpoint written by the REFERENCE (argparse.Namespace args, torch SGD state, DataParallel key form) loads too
+    ref_opt = torch.optim.SGD(build_model(net, nd, st).parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    ref_args = argparse.Namespace(lr=0.1, beta1=0.9, wd=5e-4, ewm=5e-3, akb=200, aew=400, apw=200, kbmc=1e-3, kbmd=1e-3, pwm=1.0, wrd=1.0,
+                                  wmf=0.4, cmi=0, dmi=2.3, epsilon=0.1, om=False, epochs=600, x_sigma=1, br=True, train_time=1)
+    ref_ck = {"epoch": 3, "args": ref_args, "optimizer": ref_opt.state_dict(),
+              "state_dict": {k.replace("encoder.pre_process.", "encoder.pre_process.module."): v for k, v in st.items()}}
+    mc = build_model(net, nd, st).train()
+    tc = Trainer(mc, B, hyper=hyper, dataset="Cifar10", adjust_lr=(1, 2, 3), use_graph=False, device_noise=False)
+    assert tc.load_checkpoint(ref_ck) == 3
+    assert tc.base_ewm == pytest.approx(1e-3)            # the reference pickles ewm AFTER its x5 at the first milestone
+    r = tc.train_epoch(lu[:1], ll[:1], 3)
+    assert r["steps"] == 1 and np.isfinite(r["kl_inference"])
