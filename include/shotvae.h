@@ -93,7 +93,7 @@ typedef struct {
   int32_t in_stride, splits;
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
-  int32_t impl;    /* 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 halo-tile kernel */
+  int32_t impl;    /* 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 (halo-tile kernel for C, N <= 128; TMA-fed kernel for wider layers) */
 } sv_wgrad_args;
 int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream);
 /* The tcgen05 kernel writes one partial slice per persistent CTA: returns the `splits` value the caller

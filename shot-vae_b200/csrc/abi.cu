@@ -168,14 +168,15 @@ static int fill_wgrad(const sv_wgrad_args* a, WgradParams& p) {
   return SV_OK;
 }
 
-static bool wgrad_uses_tc(const sv_wgrad_args* a, const WgradParams& p) {
+// 0 = mma.sync kernel, 2 = tcgen05 halo-tile kernel (narrow layers), 3 = tcgen05 + TMA kernel (wide layers)
+static int wgrad_kernel(const sv_wgrad_args* a, const WgradParams& p) {
 #ifndef SV_NO_TCGEN05
-  if (a->impl == 1) return false;
-  if (a->impl == 0 && !auto_tc_enabled()) return false;
-  return wgrad_halo_supported(p);
-#else
-  return false;
+  if (a->impl == 1) return 0;
+  if (a->impl == 0 && !auto_tc_enabled()) return 0;
+  if (wgrad_halo_supported(p)) return 2;
+  if (wgrad_tc_supported(p)) return 3;
 #endif
+  return 0;
 }
 
 int sv_igemm_wgrad_splits(const sv_wgrad_args* a) {
@@ -184,7 +185,9 @@ int sv_igemm_wgrad_splits(const sv_wgrad_args* a) {
   if (tmp.splits < 1) tmp.splits = 1;
   if (fill_wgrad(&tmp, p) != SV_OK) return 0;
 #ifndef SV_NO_TCGEN05
-  if (wgrad_uses_tc(a, p)) return wgrad_halo_splits(p);
+  const int k = wgrad_kernel(a, p);
+  if (k == 2) return wgrad_halo_splits(p);
+  if (k == 3) return wgrad_tc_splits(p);
 #endif
   return 0;
 }
@@ -194,8 +197,10 @@ int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream) {
   int rc = fill_wgrad(a, p);
   if (rc != SV_OK) return rc;
 #ifndef SV_NO_TCGEN05
-  if (wgrad_uses_tc(a, p)) return wgrad_halo(p, (cudaStream_t)stream);
-  SV_REQUIRE(a->impl != 2, "sv_igemm_wgrad: shape not supported by the tcgen05 kernel");
+  const int k = wgrad_kernel(a, p);
+  if (k == 2) return wgrad_halo(p, (cudaStream_t)stream);
+  if (k == 3) return wgrad_tc(p, (cudaStream_t)stream);
+  SV_REQUIRE(a->impl != 2, "sv_igemm_wgrad: shape not supported by the tcgen05 kernels");
 #endif
   return igemm_wgrad_mma(p, (cudaStream_t)stream);
 }

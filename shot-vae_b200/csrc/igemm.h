@@ -69,3 +69,7 @@ int igemm_fprop_halo(const IgemmParams& p, cudaStream_t st);
 bool wgrad_halo_supported(const WgradParams& p);
 int wgrad_halo_splits(const WgradParams& p);
 int wgrad_halo(const WgradParams& p, cudaStream_t st);
+// tcgen05 + TMA weight gradient for wide layers (wgrad_tc.cu)
+bool wgrad_tc_supported(const WgradParams& p);
+int wgrad_tc_splits(const WgradParams& p);
+int wgrad_tc(const WgradParams& p, cudaStream_t st);

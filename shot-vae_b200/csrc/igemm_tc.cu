@@ -184,10 +184,12 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
         for (int kb = 0; kb < KT; ++kb, ++g) {
           const int la = (2 * g) % N_PRODUCERS;
           const bool do_a = la == prod, do_b = (la + 1) % N_PRODUCERS == prod;
+          const int stage = g % p.stages;
+          // every producer observes every release of every stage in order (a parity wait cannot tell phases two apart: a
+          // producer that skipped uses of a stage must not get ahead of it -- see wgrad_tc.cu)
+          mbar_wait(&empty_bar[stage], (uint32_t)(((g / p.stages) & 1) ^ 1));
           if (!do_a && !do_b) continue;
           const int t = kb / p.KC, cb = kb - t * p.KC;
-          const int stage = g % p.stages;
-          mbar_wait(&empty_bar[stage], (uint32_t)(((g / p.stages) & 1) ^ 1));
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           if (do_a) {
             mbar_expect_tx(&full_bar[stage], a_bytes);

@@ -231,7 +231,9 @@ def test_conv_dgrad_phases_match_autograd(sv, impl, cin, cout, H, stride, k, NB)
 
 @pytest.mark.parametrize("impl", [2, 3])
 @pytest.mark.parametrize("cin,cout,H,k,NB,G,slope", [(32, 32, 32, 3, 64, 2, 0.01), (64, 64, 16, 3, 128, 4, 0.01), (128, 128, 8, 3, 256, 4, 0.0),
-                                                     (32, 16, 32, 1, 40, 1, 1.0), (32, 32, 32, 3, 512, 4, 0.01), (160, 160, 8, 3, 16, 2, 0.01)])
+                                                     (32, 16, 32, 1, 40, 1, 1.0), (32, 32, 32, 3, 512, 4, 0.01), (160, 160, 8, 3, 16, 2, 0.01),
+                                                     (640, 640, 8, 3, 64, 4, 0.01), (320, 320, 16, 3, 32, 4, 0.01), (160, 160, 32, 3, 16, 2, 0.01),
+                                                     (512, 512, 4, 3, 64, 2, 0.0)])
 def test_dgrad_epilogue_accumulates_bn_backward_statistics(sv, impl, cin, cout, H, k, NB, G, slope):
     """input-gradient conv with the fused BatchNorm-backward statistics epilogue == the same conv followed by
     sv_bn_bwd_reduce on its (bf16) output; (cin -> cout is the FORWARD conv: the launch maps cout gradients to cin)"""
@@ -300,7 +302,11 @@ def wgrad(sv, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, grad, n_real, c_r
 @pytest.mark.parametrize("cin,cout,H,stride,k,NB,splits", [(32, 32, 16, 1, 3, 4, 3), (32, 64, 32, 2, 3, 4, 5), (16, 32, 16, 1, 1, 4, 1),
                                                            (128, 128, 8, 1, 3, 8, 2), (160, 160, 8, 1, 3, 2, 1), (16, 16, 32, 1, 3, 2, 7),
                                                            (32, 32, 32, 1, 3, 6, 1), (64, 64, 16, 1, 3, 9, 1), (16, 32, 32, 1, 3, 3, 1),
-                                                           (64, 128, 8, 1, 1, 5, 1)])
+                                                           (64, 128, 8, 1, 1, 5, 1),
+                                                           # wide layers (WRN-28-10, PreActResNet18): TMA-fed tcgen05 kernel
+                                                           (160, 160, 32, 1, 3, 4, 1), (320, 320, 16, 1, 3, 8, 1), (640, 640, 8, 1, 3, 16, 1),
+                                                           (160, 160, 8, 1, 3, 32, 1), (256, 256, 8, 1, 3, 8, 1), (512, 512, 4, 1, 3, 32, 1),
+                                                           (64, 160, 16, 1, 1, 4, 1), (160, 320, 16, 1, 1, 2, 1)])
 def test_conv_wgrad_matches_autograd(sv, impl, cin, cout, H, stride, k, NB, splits):
     from shotvae_b200.plan import conv_taps
     torch.manual_seed(11 + cin + stride + k)
