@@ -184,12 +184,16 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
         for (int kb = 0; kb < KT; ++kb, ++g) {
           const int la = (2 * g) % N_PRODUCERS;
           const bool do_a = la == prod, do_b = (la + 1) % N_PRODUCERS == prod;
-          const int stage = g % p.stages;
-          // every producer observes every release of every stage in order (a parity wait cannot tell phases two apart: a
-          // producer that skipped uses of a stage must not get ahead of it -- see wgrad_tc.cu)
-          mbar_wait(&empty_bar[stage], (uint32_t)(((g / p.stages) & 1) ^ 1));
           if (!do_a && !do_b) continue;
           const int t = kb / p.KC, cb = kb - t * p.KC;
+          const int stage = g % p.stages;
+          // A parity wait only tells the current phase from the previous one.  This producer last waited three k-blocks ago,
+          // for k-block g - 3 - stages to be consumed, so the barrier it looks at now is at most one phase behind what it asks
+          // for as long as stages >= 4 (host-side guarantee) -- and it can never be ahead, because this stage cannot be
+          // consumed again without the load issued below.  (Waiting at k-blocks a producer does NOT load for is wrong the
+          // other way round: the thread blocks ~700 cycles in each TMA issue, the barrier can flip twice meanwhile, and the
+          // stale parity then reads as "not yet" -> deadlock; MEASURED.)
+          mbar_wait(&empty_bar[stage], (uint32_t)(((g / p.stages) & 1) ^ 1));
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           if (do_a) {
             mbar_expect_tx(&full_bar[stage], a_bytes);
@@ -488,7 +492,7 @@ static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtenso
   const size_t stage_bytes = ((size_t)BM * q.KB * 2 + (size_t)q.BN * q.KB * 2 + 1023) & ~(size_t)1023;
   int stages = (int)((192 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
-  if (stages < 2) { sv_set_error("igemm_fprop_tc: tile too large"); return SV_ERR_UNSUPPORTED; }
+  if (stages < 4) { sv_set_error("igemm_fprop_tc: tile too large (the producers' parity protocol needs >= 4 stages)"); return SV_ERR_UNSUPPORTED; }
   q.stages = stages;
   memcpy(q.dy, p.dy, SV_MAX_TAPS);
   memcpy(q.dx, p.dx, SV_MAX_TAPS);

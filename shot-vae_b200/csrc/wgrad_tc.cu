@@ -13,17 +13,20 @@
 // (pairs x cb columns) stay in TMEM for the whole launch, and a slice of the pixel blocks (split-K over CTAs); the
 // partial sums are written once at the end and summed by sv_wgrad_reduce.
 //
-// warp roles: 1 = MMA issuer, 4..7 = final epilogue, 0 / 2 / 3 / 8 / 9 / 10 = TMA producers (2 allocates TMEM).  Loads are
-// dealt round-robin to the six producers because tensor-map loads issued by one thread do not overlap
-// (tools/tma_probe.cu: ~700 cycles each whatever the box size).
+// warp roles: 1 = MMA issuer, 4..7 = final epilogue, 0 / 2 / 3 / 8..12 = eight TMA producers (2 allocates TMEM).  Tensor-map
+// loads issued by one thread do not overlap (tools/tma_probe.cu: ~700 cycles each whatever the box size), so every box of a
+// stage has its own producer: producer 4*stage + b loads box b of EVERY use of that stage (G box b and A box b).  Owning
+// a fixed slot matters for correctness, not only for speed: an mbarrier parity wait can only tell the current phase from
+// the previous one, so a thread must neither skip uses of a barrier (it could run two phases ahead -- found with
+// compute-sanitizer as an over-arrival) nor wait on uses it does not load for (it blocks in its own TMA issue meanwhile and
+// can fall two phases behind -- found as a deadlock in igemm_tc.cu).
 #include <cuda.h>
 #include "common.cuh"
 #include "igemm.h"
 
 namespace {
 
-constexpr int WT_THREADS = 384;
-constexpr int N_PRODUCERS = 6;
+constexpr int WT_THREADS = 416;
 constexpr int BLK = 128;                 // pixels per block = channels per n-tile
 constexpr uint32_t BOX_BYTES = 64 * BLK * 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
@@ -140,35 +143,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  const int prod = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : (warp >= 8 && warp <= 10 ? warp - 5 : -1)));
+  const int prod = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : (warp >= 8 && warp <= 12 ? warp - 5 : -1)));
   if (prod >= 0) {
     // ===================================== TMA producers =====================================
-    if (lane == 0) {
+    const int ps = prod >> 2, pbx = prod & 3;       // the stage and the box slot this producer owns
+    if (lane == 0 && (pbx < p.boxes || pbx < 2)) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      long long L = 0;          // running load number: issued by producer L % N_PRODUCERS
       int gi = 0, ai = 0;       // G stages / A stages filled so far
       for (int pb = pb0; pb < pb1; ++pb, ++gi) {
         const int img0 = (pb / p.tiles_h) * p.Nt, h0 = (pb % p.tiles_h) * p.Ht;
-        const int gs = gi & 1;
-        // EVERY producer observes EVERY release of a stage, in order, whether or not it issues a box of this use: a parity
-        // wait only tells the current phase from the previous one, and with two stages a producer that skipped a use could be
-        // two phases ahead of the barrier and sail through (found with compute-sanitizer: over-arrival on a_full)
-        mbar_wait(&g_empty[gs], (uint32_t)(((gi >> 1) & 1) ^ 1));
-        for (int b = 0; b < 2; ++b, ++L) {
-          if ((int)(L % N_PRODUCERS) != prod) continue;
-          mbar_expect_tx(&g_full[gs], BOX_BYTES);
-          tma_load_4d(g_base + gs * g_stage + b * BOX_BYTES, &tmG, &g_full[gs], nt * BLK + 64 * b, 0, h0, img0);
+        if ((gi & 1) == ps && pbx < 2) {
+          mbar_wait(&g_empty[ps], (uint32_t)(((gi >> 1) & 1) ^ 1));
+          mbar_expect_tx(&g_full[ps], BOX_BYTES);
+          tma_load_4d(g_base + ps * g_stage + pbx * BOX_BYTES, &tmG, &g_full[ps], nt * BLK + 64 * pbx, 0, h0, img0);
         }
         for (int pr = 0; pr < npair; ++pr, ++ai) {
+          if ((ai & 1) != ps || pbx >= p.boxes) continue;
           const int pair = pair0 + pr, t = pair / p.c_blocks, cblk = pair - t * p.c_blocks;
-          const int as = ai & 1;
-          mbar_wait(&a_empty[as], (uint32_t)(((ai >> 1) & 1) ^ 1));
-          for (int b = 0; b < p.boxes; ++b, ++L) {
-            if ((int)(L % N_PRODUCERS) != prod) continue;
-            mbar_expect_tx(&a_full[as], BOX_BYTES);
-            tma_load_4d(a_base + as * a_stage + b * BOX_BYTES, &tmA, &a_full[as], cblk * p.cb + 64 * b, (int)p.dx[t], h0 + (int)p.dy[t], img0);
-          }
+          mbar_wait(&a_empty[ps], (uint32_t)(((ai >> 1) & 1) ^ 1));
+          mbar_expect_tx(&a_full[ps], BOX_BYTES);
+          tma_load_4d(a_base + ps * a_stage + pbx * BOX_BYTES, &tmA, &a_full[ps], cblk * p.cb + 64 * pbx, (int)p.dx[t], h0 + (int)p.dy[t], img0);
         }
       }
     }

@@ -6,7 +6,8 @@ vae.py:108-133, decoder.py:63-64): instead of scatter / replicate / gather throu
 block of every forward, each rank owns a replica and a batch shard, BatchNorm statistics stay per
 replica (DataParallel's semantics), and the only exchange is one sum of the gradient arena per step
 (the SGD kernel divides by world_size).  Buckets follow the order in which the last backward
-finalises gradients: the decoder range (88 % of the bytes) first, then encoder + heads.
+finalises gradients: the decoder range (88 % of the bytes) first, then the encoder block by block (last resolution block +
+heads first), each all-reduce running beside the next block's backward.
 
 Replicas start identical: construction broadcasts rank 0's parameters, BatchNorm buffers and momentum
 (nn.DataParallel gets that for free from its single master copy; torch DDP does the same broadcast).
@@ -35,6 +36,15 @@ class GradReducer:
             all(o >= split for k, (o, _, _) in net.poff.items() if k.startswith("feature_reconstructor.")), \
             "decoder parameters are not the contiguous tail of the parameter arena"
         self.buckets = {"encoder": (0, split), "decoder": (split, net.n_params)}
+        # the encoder range by backward segment (plan.Net.bwd_segments: last resolution block + transition + heads first, the
+        # first block + conv0 last), so that each piece is reduced while the next segment of the backward still runs and only
+        # the small first-block range (0.3 MB for WRN-28-2) is left exposed in front of the optimizer
+        self.segments = []
+        if hasattr(net, "segment_param_ranges"):
+            for i, rng in enumerate(net.segment_param_ranges()):
+                self.buckets["enc%d" % i] = rng
+                self.segments.append("enc%d" % i)
+            assert sum(e - s for s, e in (self.buckets[k] for k in self.segments)) == split, "encoder segments do not tile the encoder range"
         self.bytes_per_step = net.n_params * 4
         if broadcast:
             self.broadcast_state()

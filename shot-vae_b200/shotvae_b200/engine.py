@@ -189,15 +189,26 @@ class TrainStep:
 
     def _sequence(self, parts=(0, 1, 2)):
         """parts: 0 = forwards, losses, backward of [P2|P4] and the decoder backward of [P1|P3] (after it the
-        decoder gradient bucket is final); 1 = rest of the backward; 2 = SGD + BatchNorm running statistics.
+        decoder gradient bucket is final); 1 = rest of the backward -- or (1, i) = its i-th segment (one resolution block of
+        the encoder, plan.Net.bwd_segments); 2 = SGD + BatchNorm running statistics.
         With several ranks the parts are separate CUDA graphs and the bucket all-reduces are issued between
         them on a side stream (NCCL is kept out of the captured graphs)."""
-        if 0 in parts:
-            self._part0()
-        if 1 in parts:
-            self._part1()
-        if 2 in parts:
-            self._part2()
+        for part in parts:
+            if part == 0:
+                self._part0()
+            elif part == 1:
+                self._part1()
+            elif part == 2:
+                self._part2()
+            else:
+                self._part1(seg=part[1])
+
+    def _ddp_plan(self):
+        """[(parts of one CUDA graph, bucket to all-reduce after it)] for a data-parallel step"""
+        segs = self.reducer.segments if self.reducer is not None else []
+        if len(segs) < 2:
+            return [((0,), "decoder"), ((1,), "encoder"), ((2,), None)]
+        return [((0,), "decoder")] + [(((1, i),), name) for i, name in enumerate(segs)] + [((2,), None)]
 
     def _part0(self):
         net, B, st = self.net, self.B, _abi.stream()
@@ -276,8 +287,11 @@ class TrainStep:
         latB = net.sample_fwd(Bc, 1, 2, self.eps[3], unif=self.unif[1])
         net.decoder_fwd(Bc, latB)
 
-    def _part1(self):
+    def _part1(self, seg=None):
         net, A, S = self.net, self.ctxA, self.ctxS
+        if seg is not None and seg > 0:
+            net.encoder_bwd(S, None, seg=seg)
+            return
         g_mu, g_ls, g_la = self._g
         dead = (not self.m2) and (not self.skip_dead_decoders)
         main = torch.cuda.current_stream()
@@ -297,7 +311,7 @@ class TrainStep:
         # heads + encoder backward of ALL pass groups at once (g.mu / g.ls / g.la of the views are slices of S's)
         D, nd = net.ldc, net.nd
         net.encoder_bwd(S, net.heads_bwd(S, S.t("g.mu", (S.NB, D), torch.float32), S.t("g.ls", (S.NB, D), torch.float32),
-                                         S.t("g.la", (S.NB, nd), torch.float32)))
+                                         S.t("g.la", (S.NB, nd), torch.float32)), seg=seg)
         if dead and self.side2 is not None:
             main.wait_stream(self.side2)
 
@@ -316,12 +330,12 @@ class TrainStep:
         if self.reducer is None:
             self._sequence()
             return
-        self._sequence((0,))
-        self.reducer.bucket_ready("decoder")      # overlaps with the rest of the backward
-        self._sequence((1,))
-        self.reducer.bucket_ready("encoder")
-        self.reducer.wait_all()
-        self._sequence((2,))
+        for parts, bucket in self._ddp_plan():
+            if bucket is None:
+                self.reducer.wait_all()
+            self._sequence(parts)
+            if bucket is not None:
+                self.reducer.bucket_ready(bucket)      # overlaps with the next part of the backward
 
     def run_resident(self):
         """one optimizer step on the inputs currently resident in the static device buffers"""
@@ -331,7 +345,7 @@ class TrainStep:
             self._run_parts_eager()
         elif self.graph is None and self._calls >= 2:
             n0 = _abi.launch_count()
-            groups = [(0, 1, 2)] if self.reducer is None else [(0,), (1,), (2,)]
+            groups = [(0, 1, 2)] if self.reducer is None else [parts for parts, _ in self._ddp_plan()]
             graphs = []
             for parts in groups:
                 g = torch.cuda.CUDAGraph()
@@ -356,12 +370,12 @@ class TrainStep:
         if self.reducer is None:
             self.graph[0].replay()
             return
-        self.graph[0].replay()
-        self.reducer.bucket_ready("decoder")
-        self.graph[1].replay()
-        self.reducer.bucket_ready("encoder")
-        self.reducer.wait_all()
-        self.graph[2].replay()
+        for g, (_, bucket) in zip(self.graph, self._ddp_plan()):
+            if bucket is None:
+                self.reducer.wait_all()
+            g.replay()
+            if bucket is not None:
+                self.reducer.bucket_ready(bucket)
 
     def load_inputs(self, image_l, label_l, image_u, label_u, draws="auto"):
         """host -> device copy of one (labelled, unlabelled) batch pair through pinned staging buffers,

@@ -245,7 +245,7 @@ class Net:
         T = len(taps)
         dst = torch.zeros(T, N, C, dtype=torch.bfloat16, device=self.device)
         layout = 0
-        if grid is not None and self.impl in (0, 3):
+        if grid is not None and self.impl in (0, 3) and os.environ.get("SHOTVAE_HALO", "1") != "0":      # (A/B switch: 0 = per-tap TMA kernel everywhere)
             a = IgemmArgs()
             a.A = a.Wt = a.out_bf16 = ptr(dst)
             a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = 128, grid[0], grid[1], C, grid[0], grid[1], N, T
@@ -560,14 +560,43 @@ class Net:
                                         _abi.stream()))
         return feat
 
-    def encoder_bwd(self, ctx, g_feat):
-        """g_feat: fp32 [NB, feat].  Accumulates every encoder parameter gradient into the grad arena."""
+    def bwd_segments(self):
+        """unit index ranges [(lo, hi), ...] of the encoder's resolution blocks in BACKWARD order (last block first): the
+        points at which a data-parallel run hands a finished gradient range to the all-reduce (ddp.GradReducer)"""
+        units = self.topo["units"]
+        starts = [i for i, u in enumerate(units) if i == 0 or u.stride == 2] + [len(units)]
+        return [(starts[i], starts[i + 1]) for i in range(len(starts) - 2, -1, -1)]
+
+    def segment_param_ranges(self):
+        """gradient-arena ranges [(lo, hi), ...] that are final after each backward segment of bwd_segments(): the first
+        one also carries the transition BatchNorm and the heads, the last one conv0"""
+        split = self.poff["feature_reconstructor.decoder.0.weight"][0]
+        units = self.topo["units"]
+        first = lambda ui: min(o for k, (o, _, _) in self.poff.items() if k.startswith(units[ui].prefix + "."))
+        segs, out, hi = self.bwd_segments(), [], split
+        for i, (lo_u, _) in enumerate(segs):
+            lo = 0 if i == len(segs) - 1 else first(lo_u)
+            out.append((lo, hi))
+            hi = lo
+        return out
+
+    def encoder_bwd(self, ctx, g_feat, seg=None):
+        """g_feat: fp32 [NB, feat].  Accumulates every encoder parameter gradient into the grad arena.
+        seg = None: the whole backward; seg = i: only segment i of bwd_segments() (segments must be run in order; the state
+        between them lives in ctx; every segment ends with the side stream joined, so it can be its own CUDA graph)."""
         topo, NB, G, B = self.topo, ctx.NB, ctx.G, ctx.B
         slope, sslope = topo["slope"], topo["shortcut_slope"]
-        eo = ctx.enc_out
-        H, Cf = eo["H"], topo["feat"]
-        g_h = ctx.t("g.h.%d.%d" % (H, Cf), (NB, H, H, Cf))
-        self._bn_bwd(ctx, "bnT", [dict(rec=eo["bnT"], g_feat=g_feat, slope=slope)], eo["h"], None, g_h, B * H * H, H * H)
+        segs = self.bwd_segments()
+        if seg is None or seg == 0:
+            eo = ctx.enc_out
+            H, Cf = eo["H"], topo["feat"]
+            g_h = ctx.t("g.h.%d.%d" % (H, Cf), (NB, H, H, Cf))
+            self._bn_bwd(ctx, "bnT", [dict(rec=eo["bnT"], g_feat=g_feat, slope=slope)], eo["h"], None, g_h, B * H * H, H * H)
+            flip = 0
+        else:
+            g_h, flip = ctx._bwd_state
+        lo_u, hi_u = (0, len(ctx.tape)) if seg is None else segs[seg]
+        last = seg is None or seg == len(segs) - 1
         # Weight gradients run on a side stream (when the engine provides one): they only need (activation, output
         # gradient), so they overlap the dgrad -> BatchNorm-backward chain of the main stream -- tensor-core bound
         # kernels next to HBM-bound ones.  Buffers shared between units by shape (g.y1.*, the two g.h flip buffers)
@@ -602,8 +631,7 @@ class Net:
             ev.record(side)
             return ev
 
-        flip = 0
-        for rec in reversed(ctx.tape):
+        for rec in reversed(ctx.tape[lo_u:hi_u]):
             u, k, Hin, Ho = rec["u"], rec["k"], rec["H"], rec["Ho"]
             rows_in, rows_out = B * Hin * Hin, B * Ho * Ho
             g_out = g_h
@@ -649,6 +677,9 @@ class Net:
             g_h = g_prev
         if side is not None:
             main.wait_stream(side)
+        ctx._bwd_state = (g_h, flip)
+        if not last:
+            return
         # conv0: weight + bias gradient (no input gradient: the input is data)
         f0 = topo["f0"]
         cin_p = pad16(self.in_ch)
