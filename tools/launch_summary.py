@@ -13,9 +13,9 @@ def short(name):
 
 
 def family(name):
-    if name.startswith("igemm_halo_kernel") or name.startswith("igemm_fprop_tc_kernel") or name.startswith("igemm_fprop_mma_kernel"):
+    if name.startswith("igemm_halo_kernel") or name.startswith("igemm_fprop_tc") or name.startswith("igemm_fprop_mma_kernel"):
         return "conv fprop/dgrad (sv_igemm_fprop)"
-    if name.startswith("wgrad_halo_kernel") or name.startswith("igemm_wgrad_mma_kernel"):
+    if name.startswith("wgrad_halo_kernel") or name.startswith("wgrad_tc_kernel") or name.startswith("igemm_wgrad_mma_kernel"):
         return "conv wgrad (sv_igemm_wgrad)"
     if name.startswith("wgrad_reduce"):
         return "wgrad reduce"
