@@ -57,8 +57,10 @@ typedef struct {
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
   int32_t impl;         /* 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 + per-tap TMA kernel,
-                           3 = tcgen05 halo-tile kernel (input read once, taps = shifted descriptors) */
-  int32_t w_layout;     /* layout of Wt: 0 = [T][N][C]; 1 = [T][C/8][N][8] (required by, and selects, kernel 3) */
+                           3 = tcgen05 halo-tile kernel (input read once, taps = shifted descriptors),
+                           4 = FP32 kernel of the parity-grade mode (see "FP32 mode" below) */
+  int32_t w_layout;     /* layout of Wt: 0 = [T][N][C]; 1 = [T][C/8][N][8] (required by, and selects, kernel 3);
+                           2 = fp32 [T][N][C] (required by, and selects, kernel 4) */
   /* Fused BatchNorm-backward statistics (input-gradient launches): when bn_y != NULL the output IS the gradient
    * w.r.t. the activated tensor a = act(scale*y + shift) of the BatchNorm whose input y (bf16, layout of out_bf16)
    * and per-group coefficients [G][N] are given here, and instead of sum / sum-of-squares the epilogue accumulates
@@ -73,7 +75,14 @@ typedef struct {
   float bn_slope, bn_eps;
 } sv_igemm_args;
 int sv_igemm_fprop(const sv_igemm_args* a, void* stream);
-/* 1 if kernel `impl` (1, 2, 3) can run this problem; impl = 0 returns the kernel auto mode selects */
+/* FP32 mode (parity-grade precision, selected per network: plan.Net(precision="fp32")).  The reference's CPU path is
+ * FP32 end to end (main_shot_vae.py:281-366 on ATen); the production kernels round conv operands to bf16.  With
+ * impl = 4 / w_layout = 2 the SAME problem description is evaluated on fp32 tensors: A, residual and Wt point to
+ * float data, out_bf16 must be NULL, out_f32 is [NB, OHf, OWf, n_valid > 0 ? n_valid : N], products and sums are fp32
+ * FMAs on the CUDA cores.  sv_igemm_wgrad with impl = 4 takes float A / Gr.  Every activation-tensor entry point below
+ * has an `_f32` twin with float tensors in place of bf16 ones (same arguments otherwise).  About 20x slower than the
+ * bf16 tensor-core path; used by the parity tests (gradients within 2e-2 of the oracle end to end), never by bench.py. */
+/* 1 if kernel `impl` (1, 2, 3, 4) can run this problem; impl = 0 returns the kernel auto mode selects */
 int sv_igemm_fprop_supports(const sv_igemm_args* a, int32_t impl);
 /* n independent problems (the output-parity phases of one transposed convolution, reference decoder.py:19-63 ->
  * nn.ConvTranspose2d(k=4, s=2, p=1)).  Up to four problems of identical geometry that run on the per-tap tcgen05
@@ -93,7 +102,8 @@ typedef struct {
   int32_t in_stride, splits;
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
-  int32_t impl;    /* 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 (halo-tile kernel for C, N <= 128; TMA-fed kernel for wider layers) */
+  int32_t impl;    /* 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 (halo-tile kernel for C, N <= 128; TMA-fed kernel for wider layers),
+                      4 = FP32 mode (A and Gr are float tensors; any splits >= 1) */
 } sv_wgrad_args;
 int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream);
 /* The tcgen05 kernel writes one partial slice per persistent CTA: returns the `splits` value the caller
@@ -106,7 +116,8 @@ int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits, int32_t N
                     const int8_t* tap_index /* host, T entries */, void* stream);
 
 /* dst(t, n, c) (bf16) = src[n*sn + c*sc + tap_index[t]*st] for n < n_real, c < c_real else 0;
- * layout 0: dst[t][n][c]; layout 1: dst[t][c/8][n][c%8] (8-channel planes, for the halo-tile kernel) */
+ * layout 0: dst[t][n][c]; layout 1: dst[t][c/8][n][c%8] (8-channel planes, for the halo-tile kernel);
+ * layout 2: dst is FLOAT [t][n][c] (FP32 mode) */
 int sv_pack_weight(const float* src, void* dst, int32_t N, int32_t C, int32_t T, int32_t n_real, int32_t c_real,
                    int64_t sn, int64_t sc, int64_t st, const int8_t* tap_index /* host */, int32_t layout, void* stream);
 /* All packs of a network in ONE launch.  `table_dev` is a device array of n_packs records
@@ -114,8 +125,11 @@ int sv_pack_weight(const float* src, void* dst, int32_t N, int32_t C, int32_t T,
  * (sv_sizeof_pack_desc() bytes each, same meaning as the sv_pack_weight arguments). */
 int sv_pack_weights_batched(const void* table_dev, int32_t n_packs, int32_t blocks_per_pack, void* stream);
 int sv_sizeof_pack_desc(void);
-/* fp32 NCHW [NB, c_real, H, W] -> bf16 NHWC [NB, H, W, C] (zero padded channels) */
+/* fp32 NCHW [NB, c_real, H, W] -> bf16 NHWC [NB, H, W, C] (zero padded channels); _f32: fp32 NHWC */
 int sv_pack_image(const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream);
+int sv_pack_image_f32(const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream);
+/* fp32 [rows, c_real] -> fp32 [rows, C] with zero padded channels (FP32 mode: ELBO gradient -> decoder backward) */
+int sv_pad_channels_f32(const float* src, float* dst, int64_t rows, int32_t c_real, int32_t C, void* stream);
 /* fp32 NHWC [NB, HW, c_real] -> fp32 NCHW [NB, c_real, HW] */
 int sv_nhwc_to_nchw_f32(const float* src, float* dst, int32_t NB, int32_t c_real, int32_t HW, void* stream);
 
@@ -165,6 +179,20 @@ int sv_bn_running_update_batched(const void* table_dev, int32_t n_bn, int32_t ma
 int sv_sizeof_run_desc(void);
 /* out[c] += sum_rows x[row][c]  (conv0 bias gradient) */
 int sv_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream);
+int sv_colsum_f32(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream);
+/* FP32-mode twins of the BatchNorm entry points above: y / a / g_a / addend / g_y are float tensors */
+int sv_bn_act_fwd_f32(const void* y, void* a, const float* scale, const float* shift, float slope, int64_t rows_per_group,
+                      int32_t G, int32_t C, void* stream);
+int sv_bn_finalize_act_fwd_f32(const void* y, void* a, const float* stats, const float* gamma, const float* beta, float count,
+                               float eps, float slope, int64_t rows_per_group, int32_t G, int32_t C, float* mean, float* var,
+                               float* scale, float* shift, void* stream);
+int sv_bn_act_gap_fwd_f32(const void* y, float* feat, const float* scale, const float* shift, float slope, int32_t NB,
+                          int32_t HW, int32_t C, int32_t group_images, void* stream);
+int sv_bn_bwd_reduce_f32(const void* g_a, const float* g_feat, const void* y, const float* scale, const float* shift,
+                         const float* mean, const float* var, float eps, float slope, int64_t rows_per_group, int32_t HW,
+                         int32_t G, int32_t C, float* dgamma, float* dbeta, void* stream);
+int sv_bn_bwd_apply_f32(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, const void* addend, void* g_y,
+                        float eps, int64_t rows_per_group, int32_t HW, int32_t G, int32_t C, void* stream);
 
 /* ---- small FP32 linears: the three inference heads (vae.py:10-15,143-145) and the k=1
  *      ConvTranspose2d decoder stem (decoder.py:13-18) ------------------------------------------- */

@@ -86,6 +86,7 @@ static bool auto_tc_enabled() {
 }
 
 static int select_impl(const IgemmParams& p) {
+  if (p.w_layout == 2) return 4;
 #ifndef SV_NO_TCGEN05
   if (p.w_layout == 1) return 3;
   if (auto_tc_enabled() && igemm_fprop_tc_supported(p)) return 2;
@@ -98,9 +99,11 @@ int sv_igemm_fprop_supports(const sv_igemm_args* a, int32_t impl) {
   if (fill_params(a, p) != SV_OK) return 0;
   if (impl == 0) {
     const int sel = select_impl(p);
+    if (sel == 4) return igemm_fprop_f32_supported(p) ? 4 : 0;
     return (p.bn_y != nullptr && sel == 1) ? 0 : sel;      // the mma.sync kernel has no fused BatchNorm-backward epilogue
   }
   if (impl == 1) return (p.w_layout == 0 && p.bn_y == nullptr) ? 1 : 0;
+  if (impl == 4) return igemm_fprop_f32_supported(p) ? 1 : 0;
 #ifndef SV_NO_TCGEN05
   if (impl == 2) return igemm_fprop_tc_supported(p) ? 1 : 0;
   if (impl == 3) return igemm_fprop_halo_supported(p) ? 1 : 0;
@@ -125,6 +128,10 @@ int sv_igemm_fprop(const sv_igemm_args* a, void* stream) {
     return igemm_fprop_halo(p, st);
   }
 #endif
+  if (impl == 4) {
+    SV_REQUIRE(igemm_fprop_f32_supported(p), "sv_igemm_fprop: the FP32 kernel needs fp32 weights (w_layout 2), an fp32 output and no fused statistics");
+    return igemm_fprop_f32(p, st);
+  }
   SV_REQUIRE(impl == 1, "sv_igemm_fprop: unknown impl %d", impl);
   SV_REQUIRE(p.bn_y == nullptr, "sv_igemm_fprop: fused BatchNorm-backward statistics are not available on the mma.sync kernel");
   SV_REQUIRE(p.w_layout == 0, "sv_igemm_fprop: plane-interleaved weights are only consumed by the halo kernel");
@@ -170,6 +177,7 @@ static int fill_wgrad(const sv_wgrad_args* a, WgradParams& p) {
 
 // 0 = mma.sync kernel, 2 = tcgen05 halo-tile kernel (narrow layers), 3 = tcgen05 + TMA kernel (wide layers)
 static int wgrad_kernel(const sv_wgrad_args* a, const WgradParams& p) {
+  if (a->impl == 4) return 4;
 #ifndef SV_NO_TCGEN05
   if (a->impl == 1) return 0;
   if (a->impl == 0 && !auto_tc_enabled()) return 0;
@@ -196,6 +204,7 @@ int sv_igemm_wgrad(const sv_wgrad_args* a, void* stream) {
   WgradParams p;
   int rc = fill_wgrad(a, p);
   if (rc != SV_OK) return rc;
+  if (a->impl == 4) return igemm_wgrad_f32(p, (cudaStream_t)stream);      // FP32 mode: A and Gr are float tensors
 #ifndef SV_NO_TCGEN05
   const int k = wgrad_kernel(a, p);
   if (k == 2) return wgrad_halo(p, (cudaStream_t)stream);

@@ -51,7 +51,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
   mean[i] = m; var[i] = v; scale[i] = sc; shift[i] = sh;
 }
 
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict__ y, bf16* __restrict__ a,
+template <typename TA>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const TA* __restrict__ y, TA* __restrict__ a,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          float slope, long long rows_per_group, long long slab_rows, int C) {
   pdl_trigger();
@@ -69,24 +70,24 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict_
   const long long r1 = min(r0 + slab_rows, rows_per_group);
   constexpr int U = 4;
   for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
-    bf16x8 q[U];
+    typename V8<TA>::raw q[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = rb + (long long)u * nrl;
-      if (r < r1) q[u] = *reinterpret_cast<const bf16x8*>(y + ((size_t)g * rows_per_group + r) * C + chunk * 8);
+      if (r < r1) q[u] = V8<TA>::load(y + ((size_t)g * rows_per_group + r) * C + chunk * 8);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = rb + (long long)u * nrl;
       if (r < r1) {
         float v[8];
-        unpack8(q[u], v);
+        V8<TA>::unpack(q[u], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float t = fmaf(v[j], sc[j], sh[j]);
           v[j] = t > 0.f ? t : slope * t;
         }
-        *reinterpret_cast<bf16x8*>(a + ((size_t)g * rows_per_group + r) * C + chunk * 8) = pack8(v);
+        V8<TA>::store(a + ((size_t)g * rows_per_group + r) * C + chunk * 8, v);
       }
     }
   }
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict_
 // BatchNorm finalize fused into the apply: every thread derives scale/shift of its 8 channels from the raw
 // (sum, sum^2) statistics; block (0, g) also publishes mean / var / scale / shift for the backward pass and
 // the running-statistics update.  Saves one launch per BatchNorm.
-__global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(const bf16* __restrict__ y, bf16* __restrict__ a,
+template <typename TA>
+__global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(const TA* __restrict__ y, TA* __restrict__ a,
                                                                   const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, float count, float eps, float slope,
                                                                   long long rows_per_group, long long slab_rows, int C, float* mean,
@@ -125,24 +127,24 @@ __global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(const bf16* __
   const long long r1 = min(r0 + slab_rows, rows_per_group);
   constexpr int U = 4;
   for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
-    bf16x8 q[U];
+    typename V8<TA>::raw q[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = rb + (long long)u * nrl;
-      if (r < r1) q[u] = *reinterpret_cast<const bf16x8*>(y + ((size_t)g * rows_per_group + r) * C + chunk * 8);
+      if (r < r1) q[u] = V8<TA>::load(y + ((size_t)g * rows_per_group + r) * C + chunk * 8);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = rb + (long long)u * nrl;
       if (r < r1) {
         float v[8];
-        unpack8(q[u], v);
+        V8<TA>::unpack(q[u], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float t = fmaf(v[j], sc[j], sh[j]);
           v[j] = t > 0.f ? t : slope * t;
         }
-        *reinterpret_cast<bf16x8*>(a + ((size_t)g * rows_per_group + r) * C + chunk * 8) = pack8(v);
+        V8<TA>::store(a + ((size_t)g * rows_per_group + r) * C + chunk * 8, v);
       }
     }
   }
@@ -174,7 +176,8 @@ __global__ void bn_running_update_batched_kernel(const RunDesc* __restrict__ tab
   d.running_var[c] = rv;
 }
 
-__global__ void __launch_bounds__(256) bn_act_gap_kernel(const bf16* __restrict__ y, float* __restrict__ feat,
+template <typename TA>
+__global__ void __launch_bounds__(256) bn_act_gap_kernel(const TA* __restrict__ y, float* __restrict__ feat,
                                                          const float* __restrict__ scale, const float* __restrict__ shift, float slope,
                                                          int NB, int HW, int C, int group_images) {
   // one CTA per image: threads = (8-channel chunk) x (pixel slice); the slices are folded through shared memory
@@ -195,11 +198,11 @@ __global__ void __launch_bounds__(256) bn_act_gap_kernel(const bf16* __restrict_
       sh[j] = shift[(size_t)g * C + chunk * 8 + j];
       acc[j] = 0.f;
     }
-    const bf16* base = y + (size_t)nb * HW * C + chunk * 8;
+    const TA* base = y + (size_t)nb * HW * C + chunk * 8;
 #pragma unroll 4
     for (int p = slice; p < HW; p += slices) {
       float v[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(base + (size_t)p * C), v);
+      V8<TA>::unpack(V8<TA>::load(base + (size_t)p * C), v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = fmaf(v[j], sc[j], sh[j]);
@@ -219,9 +222,9 @@ __global__ void __launch_bounds__(256) bn_act_gap_kernel(const bf16* __restrict_
 }
 
 // dgamma/dbeta reduction
-template <bool FEAT>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ g_a, const float* __restrict__ g_feat,
-                                                            const bf16* __restrict__ y, const float* __restrict__ scale,
+template <bool FEAT, typename TA>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const TA* __restrict__ g_a, const float* __restrict__ g_feat,
+                                                            const TA* __restrict__ y, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, const float* __restrict__ mean,
                                                             const float* __restrict__ var, float eps, float slope,
                                                             long long rows_per_group, long long slab_rows, int HW, int C,
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
   const long long r1 = min(r0 + slab_rows, rows_per_group);
   constexpr int U = 4;      // rows in flight per thread (memory-level parallelism)
   for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
-    bf16x8 gq[U], yq[U];
+    typename V8<TA>::raw gq[U], yq[U];
     float gf[U][8];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -258,9 +261,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 #pragma unroll
           for (int j = 0; j < 8; ++j) gf[u][j] = g_feat[nb * C + chunk * 8 + j] * inv_hw;
         } else {
-          gq[u] = *reinterpret_cast<const bf16x8*>(g_a + off);
+          gq[u] = V8<TA>::load(g_a + off);
         }
-        yq[u] = *reinterpret_cast<const bf16x8*>(y + off);
+        yq[u] = V8<TA>::load(y + off);
       }
     }
 #pragma unroll
@@ -272,9 +275,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 #pragma unroll
           for (int j = 0; j < 8; ++j) gv[j] = gf[u][j];
         } else {
-          unpack8(gq[u], gv);
+          V8<TA>::unpack(gq[u], gv);
         }
-        unpack8(yq[u], yv);
+        V8<TA>::unpack(yq[u], yv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float pre = fmaf(yv[j], sc[j], sh[j]);
@@ -305,9 +308,9 @@ struct BwdTerms {
 
 // NT = number of BatchNorm branches fed by y (2 only at a residual unit with a projection shortcut).  The
 // single-branch instantiation keeps half the per-channel coefficients, fits 2 CTAs per SM and streams faster.
-template <int NT>
-__global__ void __launch_bounds__(256, NT == 1 ? 2 : 1) bn_bwd_apply_kernel(const BwdTerms T, const bf16* __restrict__ y,
-                                                           const bf16* __restrict__ addend, bf16* __restrict__ g_y, float eps,
+template <int NT, typename TA>
+__global__ void __launch_bounds__(256, (NT == 1 && sizeof(TA) == 2) ? 2 : 1) bn_bwd_apply_kernel(const BwdTerms T, const TA* __restrict__ y,
+                                                           const TA* __restrict__ addend, TA* __restrict__ g_y, float eps,
                                                            long long rows_per_group, long long slab_rows, int HW, int G, int C) {
   pdl_trigger();
   pdl_wait();
@@ -351,17 +354,17 @@ __global__ void __launch_bounds__(256, NT == 1 ? 2 : 1) bn_bwd_apply_kernel(cons
   const long long r1 = min(r0 + slab_rows, rows_per_group);
   constexpr int U = 4;      // rows in flight per thread
   for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
-    bf16x8 yq[U], aq[U], gq[NT][U];
+    typename V8<TA>::raw yq[U], aq[U], gq[NT][U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = rb + (long long)u * nrl;
       if (r < r1) {
         const size_t off = ((size_t)g * rows_per_group + r) * C + chunk * 8;
-        yq[u] = *reinterpret_cast<const bf16x8*>(y + off);
-        if (addend != nullptr) aq[u] = *reinterpret_cast<const bf16x8*>(addend + off);
+        yq[u] = V8<TA>::load(y + off);
+        if (addend != nullptr) aq[u] = V8<TA>::load(addend + off);
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-          if (t < T.n && T.t[t].g_feat == nullptr) gq[t][u] = *reinterpret_cast<const bf16x8*>((const bf16*)T.t[t].g_a + off);
+          if (t < T.n && T.t[t].g_feat == nullptr) gq[t][u] = V8<TA>::load((const TA*)T.t[t].g_a + off);
       }
     }
 #pragma unroll
@@ -371,9 +374,9 @@ __global__ void __launch_bounds__(256, NT == 1 ? 2 : 1) bn_bwd_apply_kernel(cons
         const size_t row = (size_t)g * rows_per_group + r;
         const size_t off = row * C + chunk * 8;
         float yv[8], o[8];
-        unpack8(yq[u], yv);
+        V8<TA>::unpack(yq[u], yv);
         if (addend != nullptr) {
-          unpack8(aq[u], o);
+          V8<TA>::unpack(aq[u], o);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = 0.f;
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(256, NT == 1 ? 2 : 1) bn_bwd_apply_kernel(cons
 #pragma unroll
               for (int j = 0; j < 8; ++j) gv[j] = T.t[t].g_feat[nb * C + chunk * 8 + j] * inv_hw;
             } else {
-              unpack8(gq[t][u], gv);
+              V8<TA>::unpack(gq[t][u], gv);
             }
             const float slope = T.t[t].slope;
 #pragma unroll
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(256, NT == 1 ? 2 : 1) bn_bwd_apply_kernel(cons
             }
           }
         }
-        *reinterpret_cast<bf16x8*>(g_y + off) = pack8(o);
+        V8<TA>::store(g_y + off, o);
       }
     }
   }
@@ -424,7 +427,8 @@ __global__ void bn_running_update_kernel(PassPtrs P, int npass, float count, flo
   running_var[c] = rv;
 }
 
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long rows,
+template <typename TA>
+__global__ void __launch_bounds__(256) colsum_kernel(const TA* __restrict__ x, float* __restrict__ out, long long rows,
                                                      long long slab_rows, int C, int c_real) {
   extern __shared__ float s_acc[];  // [C]
   const int cpr = C / 8;
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   const long long r1 = min(r0 + slab_rows, rows);
   for (long long r = r0 + rl; r < r1; r += nrl) {
     float v[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(x + (size_t)r * C + chunk * 8), v);
+    V8<TA>::unpack(V8<TA>::load(x + (size_t)r * C + chunk * 8), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] += v[j];
   }
@@ -448,7 +452,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   for (int i = threadIdx.x; i < c_real; i += blockDim.x) atomicAdd(&out[i], s_acc[i]);
 }
 
-__global__ void pack_image_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long npix, int c_real, int HW,
+template <typename TA>
+__global__ void pack_image_kernel(const float* __restrict__ src, TA* __restrict__ dst, long long npix, int c_real, int HW,
                                   int C) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= npix) return;
@@ -460,8 +465,17 @@ __global__ void pack_image_kernel(const float* __restrict__ src, bf16* __restric
       const int c = c0 + j;
       v[j] = c < c_real ? src[((size_t)nb * c_real + c) * HW + p] : 0.f;
     }
-    *reinterpret_cast<bf16x8*>(dst + (size_t)i * C + c0) = pack8(v);
+    V8<TA>::store(dst + (size_t)i * C + c0, v);
   }
+}
+
+// fp32 [rows][c_real] -> fp32 [rows][C], zero padded channels (FP32 mode: the ELBO gradient enters the decoder backward)
+__global__ void pad_channels_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long total, int c_real, int C) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  dst[i] = c < c_real ? src[r * c_real + c] : 0.f;
 }
 
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, long long total, int c_real,
@@ -473,6 +487,95 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
   const int c = (int)(r % c_real);
   const long long nb = r / c_real;
   dst[i] = src[((size_t)nb * HW + p) * c_real + c];
+}
+
+
+// ---- host launchers, templated on the activation element type (bf16: production; float: parity-grade FP32 mode) ----
+template <typename TA>
+int bn_act_fwd_t(const void* y, void* a, const float* scale, const float* shift, float slope, int64_t rows_per_group, int32_t G,
+                 int32_t C, void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_act_fwd: unsupported C=%d", C);
+  const ColShape s = col_shape(rows_per_group, G, C, 4);
+  sv_launch_pdl(bn_act_fwd_kernel<TA>, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, (const TA*)y, (TA*)a, scale, shift, slope,
+                (long long)rows_per_group, s.slab_rows, C);
+  return sv_check_launch("bn_act_fwd");
+}
+
+template <typename TA>
+int bn_finalize_act_fwd_t(const void* y, void* a, const float* stats, const float* gamma, const float* beta, float count, float eps,
+                          float slope, int64_t rows_per_group, int32_t G, int32_t C, float* mean, float* var, float* scale, float* shift,
+                          void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_finalize_act_fwd: unsupported C=%d", C);
+  SV_REQUIRE(y && a && stats && gamma && beta && mean && var && scale && shift, "sv_bn_finalize_act_fwd: null pointer");
+  const ColShape s = col_shape(rows_per_group, G, C, 4);
+  sv_launch_pdl(bn_finalize_act_fwd_kernel<TA>, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, (const TA*)y, (TA*)a, stats, gamma,
+                beta, count, eps, slope, (long long)rows_per_group, s.slab_rows, C, mean, var, scale, shift);
+  return sv_check_launch("bn_finalize_act_fwd");
+}
+
+template <typename TA>
+int bn_act_gap_fwd_t(const void* y, float* feat, const float* scale, const float* shift, float slope, int32_t NB, int32_t HW, int32_t C,
+                     int32_t group_images, void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_act_gap_fwd: unsupported C=%d", C);
+  const int cpr = C / 8, slices = 256 / cpr;
+  const size_t smem = (size_t)slices * C * sizeof(float);
+  sv_launch_pdl(bn_act_gap_kernel<TA>, dim3(NB), dim3(256), smem, (cudaStream_t)stream, (const TA*)y, feat, scale, shift, slope, NB, HW, C,
+                group_images);
+  return sv_check_launch("bn_act_gap");
+}
+
+template <typename TA>
+int bn_bwd_reduce_t(const void* g_a, const float* g_feat, const void* y, const float* scale, const float* shift, const float* mean,
+                    const float* var, float eps, float slope, int64_t rows_per_group, int32_t HW, int32_t G, int32_t C, float* dgamma,
+                    float* dbeta, void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_bwd_reduce: unsupported C=%d", C);
+  SV_REQUIRE((g_a != nullptr) != (g_feat != nullptr), "sv_bn_bwd_reduce: exactly one of g_a / g_feat");
+  const ColShape s = col_shape(rows_per_group, G, C, 2);   // few blocks: each ends with 2*C global atomics
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  if (g_feat)
+    sv_launch_pdl(bn_bwd_reduce_kernel<true, TA>, dim3(s.slabs, G), dim3(s.threads), smem, (cudaStream_t)stream, (const TA*)nullptr, g_feat,
+                  (const TA*)y, scale, shift, mean, var, eps, slope, (long long)rows_per_group, s.slab_rows, HW, C, dgamma, dbeta);
+  else
+    sv_launch_pdl(bn_bwd_reduce_kernel<false, TA>, dim3(s.slabs, G), dim3(s.threads), smem, (cudaStream_t)stream, (const TA*)g_a,
+                  (const float*)nullptr, (const TA*)y, scale, shift, mean, var, eps, slope, (long long)rows_per_group, s.slab_rows, HW, C,
+                  dgamma, dbeta);
+  return sv_check_launch("bn_bwd_reduce");
+}
+
+template <typename TA>
+int bn_bwd_apply_t(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, const void* addend, void* g_y, float eps,
+                   int64_t rows_per_group, int32_t HW, int32_t G, int32_t C, void* stream) {
+  SV_REQUIRE(nterms >= 1 && nterms <= 2, "sv_bn_bwd_apply: nterms must be 1 or 2");
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_bwd_apply: unsupported C=%d", C);
+  BwdTerms T;
+  memset(&T, 0, sizeof(T));
+  T.n = nterms;
+  for (int i = 0; i < nterms; ++i) T.t[i] = terms[i];
+  const ColShape s = col_shape(rows_per_group, G, C, 4);
+  if (nterms == 1)
+    sv_launch_pdl(bn_bwd_apply_kernel<1, TA>, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, T, (const TA*)y, (const TA*)addend,
+                  (TA*)g_y, eps, (long long)rows_per_group, s.slab_rows, HW, G, C);
+  else
+    sv_launch_pdl(bn_bwd_apply_kernel<2, TA>, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, T, (const TA*)y, (const TA*)addend,
+                  (TA*)g_y, eps, (long long)rows_per_group, s.slab_rows, HW, G, C);
+  return sv_check_launch("bn_bwd_apply");
+}
+
+template <typename TA>
+int colsum_t(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream) {
+  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_colsum: unsupported C=%d", C);
+  const ColShape s = col_shape(rows, 1, C);
+  colsum_kernel<TA><<<s.slabs, s.threads, (size_t)C * sizeof(float), (cudaStream_t)stream>>>((const TA*)x, out, (long long)rows, s.slab_rows, C,
+                                                                                             c_real);
+  return sv_check_launch("colsum");
+}
+
+template <typename TA>
+int pack_image_t(const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream) {
+  SV_REQUIRE(C % 8 == 0, "sv_pack_image: C %% 8");
+  const long long npix = (long long)NB * HW;
+  pack_image_kernel<TA><<<(int)ceil_div_ll(npix, 256), 256, 0, (cudaStream_t)stream>>>(src, (TA*)dst, npix, c_real, HW, C);
+  return sv_check_launch("pack_image");
 }
 
 }  // namespace
@@ -488,24 +591,42 @@ int sv_bn_finalize(const float* stats, const float* gamma, const float* beta, fl
   return sv_check_launch("bn_finalize");
 }
 
-int sv_bn_act_fwd(const void* y, void* a, const float* scale, const float* shift, float slope, int64_t rows_per_group,
-                  int32_t G, int32_t C, void* stream) {
-  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_act_fwd: unsupported C=%d", C);
-  const ColShape s = col_shape(rows_per_group, G, C, 4);
-  sv_launch_pdl(bn_act_fwd_kernel, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, (const bf16*)y, (bf16*)a, scale, shift, slope,
-                                                                              rows_per_group, s.slab_rows, C);
-  return sv_check_launch("bn_act_fwd");
-}
+// every activation-tensor entry point exists twice: bf16 tensors (production) and fp32 tensors (`_f32`, the parity-grade mode)
+#define SV_BN_PAIR(name, impl, params, args)                         \
+  int name params { return impl<bf16> args; }                       \
+  int name##_f32 params { return impl<float> args; }
 
-int sv_bn_finalize_act_fwd(const void* y, void* a, const float* stats, const float* gamma, const float* beta, float count, float eps,
-                           float slope, int64_t rows_per_group, int32_t G, int32_t C, float* mean, float* var, float* scale,
-                           float* shift, void* stream) {
-  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_finalize_act_fwd: unsupported C=%d", C);
-  SV_REQUIRE(y && a && stats && gamma && beta && mean && var && scale && shift, "sv_bn_finalize_act_fwd: null pointer");
-  const ColShape s = col_shape(rows_per_group, G, C, 4);
-  sv_launch_pdl(bn_finalize_act_fwd_kernel, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, 
-      (const bf16*)y, (bf16*)a, stats, gamma, beta, count, eps, slope, rows_per_group, s.slab_rows, C, mean, var, scale, shift);
-  return sv_check_launch("bn_finalize_act_fwd");
+SV_BN_PAIR(sv_bn_act_fwd, bn_act_fwd_t,
+           (const void* y, void* a, const float* scale, const float* shift, float slope, int64_t rows_per_group, int32_t G, int32_t C,
+            void* stream),
+           (y, a, scale, shift, slope, rows_per_group, G, C, stream))
+SV_BN_PAIR(sv_bn_finalize_act_fwd, bn_finalize_act_fwd_t,
+           (const void* y, void* a, const float* stats, const float* gamma, const float* beta, float count, float eps, float slope,
+            int64_t rows_per_group, int32_t G, int32_t C, float* mean, float* var, float* scale, float* shift, void* stream),
+           (y, a, stats, gamma, beta, count, eps, slope, rows_per_group, G, C, mean, var, scale, shift, stream))
+SV_BN_PAIR(sv_bn_act_gap_fwd, bn_act_gap_fwd_t,
+           (const void* y, float* feat, const float* scale, const float* shift, float slope, int32_t NB, int32_t HW, int32_t C,
+            int32_t group_images, void* stream),
+           (y, feat, scale, shift, slope, NB, HW, C, group_images, stream))
+SV_BN_PAIR(sv_bn_bwd_reduce, bn_bwd_reduce_t,
+           (const void* g_a, const float* g_feat, const void* y, const float* scale, const float* shift, const float* mean,
+            const float* var, float eps, float slope, int64_t rows_per_group, int32_t HW, int32_t G, int32_t C, float* dgamma,
+            float* dbeta, void* stream),
+           (g_a, g_feat, y, scale, shift, mean, var, eps, slope, rows_per_group, HW, G, C, dgamma, dbeta, stream))
+SV_BN_PAIR(sv_bn_bwd_apply, bn_bwd_apply_t,
+           (const sv_bn_bwd_term* terms, int32_t nterms, const void* y, const void* addend, void* g_y, float eps, int64_t rows_per_group,
+            int32_t HW, int32_t G, int32_t C, void* stream),
+           (terms, nterms, y, addend, g_y, eps, rows_per_group, HW, G, C, stream))
+SV_BN_PAIR(sv_pack_image, pack_image_t,
+           (const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream),
+           (src, dst, NB, c_real, HW, C, stream))
+#undef SV_BN_PAIR
+
+int sv_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream) {
+  return colsum_t<bf16>(x, out, rows, C, c_real, stream);
+}
+int sv_colsum_f32(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream) {
+  return colsum_t<float>(x, out, rows, C, c_real, stream);
 }
 
 int sv_sizeof_run_desc(void) { return (int)sizeof(RunDesc); }
@@ -514,51 +635,6 @@ int sv_bn_running_update_batched(const void* table_dev, int32_t n_bn, int32_t ma
   SV_REQUIRE(table_dev && n_bn > 0 && max_c > 0, "sv_bn_running_update_batched: bad arguments");
   bn_running_update_batched_kernel<<<dim3(ceil_div(max_c, 128), n_bn), 128, 0, (cudaStream_t)stream>>>((const RunDesc*)table_dev, momentum);
   return sv_check_launch("bn_running_update_batched");
-}
-
-int sv_bn_act_gap_fwd(const void* y, float* feat, const float* scale, const float* shift, float slope, int32_t NB, int32_t HW,
-                      int32_t C, int32_t group_images, void* stream) {
-  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_act_gap_fwd: unsupported C=%d", C);
-  const int cpr = C / 8, slices = 256 / cpr;
-  const size_t smem = (size_t)slices * C * sizeof(float);
-  sv_launch_pdl(bn_act_gap_kernel, dim3(NB), dim3(256), smem, (cudaStream_t)stream, (const bf16*)y, feat, scale, shift, slope, NB, HW, C,
-                group_images);
-  return sv_check_launch("bn_act_gap");
-}
-
-int sv_bn_bwd_reduce(const void* g_a, const float* g_feat, const void* y, const float* scale, const float* shift,
-                     const float* mean, const float* var, float eps, float slope, int64_t rows_per_group, int32_t HW,
-                     int32_t G, int32_t C, float* dgamma, float* dbeta, void* stream) {
-  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_bwd_reduce: unsupported C=%d", C);
-  SV_REQUIRE((g_a != nullptr) != (g_feat != nullptr), "sv_bn_bwd_reduce: exactly one of g_a / g_feat");
-  const ColShape s = col_shape(rows_per_group, G, C, 2);   // few blocks: each ends with 2*C global atomics
-  const size_t smem = 2 * (size_t)C * sizeof(float);
-  if (g_feat)
-    sv_launch_pdl(bn_bwd_reduce_kernel<true>, dim3(s.slabs, G), dim3(s.threads), smem, (cudaStream_t)stream, 
-        nullptr, g_feat, (const bf16*)y, scale, shift, mean, var, eps, slope, rows_per_group, s.slab_rows, HW, C, dgamma, dbeta);
-  else
-    sv_launch_pdl(bn_bwd_reduce_kernel<false>, dim3(s.slabs, G), dim3(s.threads), smem, (cudaStream_t)stream, 
-        (const bf16*)g_a, nullptr, (const bf16*)y, scale, shift, mean, var, eps, slope, rows_per_group, s.slab_rows, HW, C,
-        dgamma, dbeta);
-  return sv_check_launch("bn_bwd_reduce");
-}
-
-int sv_bn_bwd_apply(const sv_bn_bwd_term* terms, int32_t nterms, const void* y, const void* addend, void* g_y, float eps,
-                    int64_t rows_per_group, int32_t HW, int32_t G, int32_t C, void* stream) {
-  SV_REQUIRE(nterms >= 1 && nterms <= 2, "sv_bn_bwd_apply: nterms must be 1 or 2");
-  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_bn_bwd_apply: unsupported C=%d", C);
-  BwdTerms T;
-  memset(&T, 0, sizeof(T));
-  T.n = nterms;
-  for (int i = 0; i < nterms; ++i) T.t[i] = terms[i];
-  const ColShape s = col_shape(rows_per_group, G, C, 4);
-  if (nterms == 1)
-    sv_launch_pdl(bn_bwd_apply_kernel<1>, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, T, (const bf16*)y, (const bf16*)addend, (bf16*)g_y, eps,
-                                                                                     rows_per_group, s.slab_rows, HW, G, C);
-  else
-    sv_launch_pdl(bn_bwd_apply_kernel<2>, dim3(s.slabs, G), dim3(s.threads), 0, (cudaStream_t)stream, T, (const bf16*)y, (const bf16*)addend, (bf16*)g_y, eps,
-                                                                                     rows_per_group, s.slab_rows, HW, G, C);
-  return sv_check_launch("bn_bwd_apply");
 }
 
 int sv_bn_running_update(const float* const* mean_ptrs, const float* const* var_ptrs, int32_t npass, float count,
@@ -572,19 +648,11 @@ int sv_bn_running_update(const float* const* mean_ptrs, const float* const* var_
   return sv_check_launch("bn_running_update");
 }
 
-int sv_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, int32_t c_real, void* stream) {
-  SV_REQUIRE(C % 8 == 0 && C / 8 <= 256, "sv_colsum_bf16: unsupported C=%d", C);
-  const ColShape s = col_shape(rows, 1, C);
-  colsum_kernel<<<s.slabs, s.threads, (size_t)C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, out, rows,
-                                                                                         s.slab_rows, C, c_real);
-  return sv_check_launch("colsum");
-}
-
-int sv_pack_image(const float* src, void* dst, int32_t NB, int32_t c_real, int32_t HW, int32_t C, void* stream) {
-  SV_REQUIRE(C % 8 == 0, "sv_pack_image: C %% 8");
-  const long long npix = (long long)NB * HW;
-  pack_image_kernel<<<(int)ceil_div_ll(npix, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, npix, c_real, HW, C);
-  return sv_check_launch("pack_image");
+int sv_pad_channels_f32(const float* src, float* dst, int64_t rows, int32_t c_real, int32_t C, void* stream) {
+  SV_REQUIRE(src && dst && c_real <= C, "sv_pad_channels_f32: bad arguments");
+  const long long total = (long long)rows * C;
+  pad_channels_f32_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, total, c_real, C);
+  return sv_check_launch("pad_channels_f32");
 }
 
 int sv_nhwc_to_nchw_f32(const float* src, float* dst, int32_t NB, int32_t c_real, int32_t HW, void* stream) {

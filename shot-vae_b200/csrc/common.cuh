@@ -129,6 +129,38 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return p;
 }
 
+// 8 consecutive channels of an activation row: bf16 (production, 16 bytes) or fp32 (parity-grade FP32 mode, 32 bytes).
+// The elementwise kernels are templated on the element type through this helper.
+template <typename T>
+struct V8;
+template <>
+struct V8<bf16> {
+  typedef bf16x8 raw;
+  static __device__ __forceinline__ raw load(const bf16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+  static __device__ __forceinline__ void unpack(const raw& r, float* f) { unpack8(r, f); }
+  static __device__ __forceinline__ void store(bf16* p, const float* f) { *reinterpret_cast<bf16x8*>(p) = pack8(f); }
+};
+struct __align__(16) f32x8 {
+  float4 a, b;
+};
+template <>
+struct V8<float> {
+  typedef f32x8 raw;
+  static __device__ __forceinline__ raw load(const float* p) {
+    raw r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+  }
+  static __device__ __forceinline__ void unpack(const raw& r, float* f) {
+    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane and instruction.  MEASURED
 // (tools/store_probe.cu): a 128-row tile of 64-byte rows costs ~600 cycles as 2 x 16-byte stores per thread
 // and ~300 as one 32-byte store; 128-byte rows 1330 -> 1010.

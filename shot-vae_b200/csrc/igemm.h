@@ -17,7 +17,7 @@ struct IgemmParams {
   int OHf, OWf, n_valid, group_images;
   int M;               // NB*OH*OW
   int rows_per_group;  // group_images*OH*OW
-  int w_layout;        // 0 = [T][N][C], 1 = [T][C/8][N][8]
+  int w_layout;        // 0 = [T][N][C], 1 = [T][C/8][N][8], 2 = fp32 [T][N][C] (FP32 mode: A / res / Wt are float tensors)
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
   // fused BatchNorm-backward statistics (see sv_igemm_args)
@@ -73,3 +73,7 @@ int wgrad_halo(const WgradParams& p, cudaStream_t st);
 bool wgrad_tc_supported(const WgradParams& p);
 int wgrad_tc_splits(const WgradParams& p);
 int wgrad_tc(const WgradParams& p, cudaStream_t st);
+// parity-grade FP32 mode (igemm_f32.cu): fp32 activations and weights, CUDA-core FMA
+bool igemm_fprop_f32_supported(const IgemmParams& p);
+int igemm_fprop_f32(const IgemmParams& p, cudaStream_t st);
+int igemm_wgrad_f32(const WgradParams& p, cudaStream_t st);

@@ -420,6 +420,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
     const int t = (int)(r / N);
     float v = 0.f;
     if (n < n_real && c < c_real) v = src[n * sn + c * sc + ti.v[t] * st];
+    if (layout == 2) {                 // fp32 [T][N][C]: operands of the parity-grade FP32 kernels (igemm_f32.cu)
+      reinterpret_cast<float*>(dst)[i] = v;
+      continue;
+    }
     const long long o = layout == 0 ? i : ((((long long)t * (C >> 3) + (c >> 3)) * N + n) << 3) + (c & 7);
     dst[o] = __float2bfloat16(v);
   }
@@ -450,7 +454,7 @@ __global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ table) 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pairs; i += (long long)nblk * blockDim.x) {
     int n, c;
     long long o;           // destination offset of tap 0; taps are NC elements apart in both layouts
-    if (d.layout == 0) {
+    if (d.layout == 0 || d.layout == 2) {
       c = (int)(i % d.C);
       n = (int)(i / d.C);
       o = i;
@@ -466,7 +470,8 @@ __global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ table) 
     const float* src = d.src + n * d.sn + c * d.sc;
     for (int t = 0; t < d.T; ++t) {
       const float v = live ? src[d.tap[t] * d.st] : 0.f;
-      d.dst[(long long)t * NC + o] = __float2bfloat16(v);
+      if (d.layout == 2) reinterpret_cast<float*>(d.dst)[(long long)t * NC + o] = v;     // fp32 [T][N][C] (FP32 mode)
+      else d.dst[(long long)t * NC + o] = __float2bfloat16(v);
     }
   }
 }
@@ -527,7 +532,7 @@ extern "C" int sv_pack_weight(const float* src, void* dst, int32_t N, int32_t C,
                               int32_t c_real, int64_t sn, int64_t sc, int64_t st, const int8_t* tap_index, int32_t layout,
                               void* stream) {
   SV_REQUIRE(T >= 1 && T <= SV_MAX_TAPS, "sv_pack_weight: bad T");
-  SV_REQUIRE(layout == 0 || (layout == 1 && C % 8 == 0), "sv_pack_weight: bad layout");
+  SV_REQUIRE(layout == 0 || layout == 2 || (layout == 1 && C % 8 == 0), "sv_pack_weight: bad layout");
   TapIdx ti;
   memcpy(ti.v, tap_index, T);
   const long long total = (long long)T * N * C;

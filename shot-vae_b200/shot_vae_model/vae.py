@@ -7,6 +7,7 @@ disc_log_alpha)` as autograd-connected CUDA tensors.  Everything between the arg
 results is libshotvae: one `torch.autograd.Function` whose forward/backward launch the sm_100a
 kernels through the C ABI.  There is no eager/PyTorch fallback -- CPU tensors raise.
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -50,7 +51,7 @@ class _VAEFunction(torch.autograd.Function):
         x = x.contiguous().float()
         cp = pad16(net.in_ch)
         x_img = ctx.t("x_img", (B, 32, 32, cp))
-        check(lib.sv_pack_image(ptr(x), ptr(x_img), B, net.in_ch, 32 * 32, cp, st))
+        check(net.fn("sv_pack_image")(ptr(x), ptr(x_img), B, net.in_ch, 32 * 32, cp, st))
         # model.eval(): BatchNorm uses the running statistics (reference valid()/test(), main_shot_vae.py:414-455);
         # everything else, including the sampling, is what the reference does in both modes
         net.eval_bn = not model.training
@@ -122,7 +123,7 @@ class _VAEFunction(torch.autograd.Function):
             cp = pad16(net.in_ch)
             g_img = ctx.t("g.rec", (B, 32, 32, cp))
             g_rec = g_rec.contiguous().float()      # (held in a variable: ptr() of a temporary would dangle)
-            check(lib.sv_pack_image(ptr(g_rec), ptr(g_img), B, net.in_ch, 32 * 32, cp, st))
+            check(net.fn("sv_pack_image")(ptr(g_rec), ptr(g_img), B, net.in_ch, 32 * 32, cp, st))
             g_lat = net.decoder_bwd(ctx, g_img)
             net.sample_bwd(ctx, 0, g_lat, gm, gl, ga, accumulate=1)
         g_feat = net.heads_bwd(ctx, gm, gl, ga)
@@ -164,6 +165,9 @@ class VariationalAutoEncoder(nn.Module):
         self._net = None
         self._ctx_pool = {}
         self._pack_version = None
+        # "bf16" (production: bf16 tensor-core operands) or "fp32" (parity-grade mode: fp32 tensors and FP32 kernels, ~20x
+        # slower; same launch sequence).  Takes effect at the next forward (the arena is re-bound).
+        self.precision = os.environ.get("SHOTVAE_PRECISION", "bf16")
         self.device_noise = False      # True: draw eps/u on the device generator (benchmark mode)
         self.noise_source = None       # optional object with randn(*shape) / rand(*shape) (parity replays)
 
@@ -181,7 +185,7 @@ class VariationalAutoEncoder(nn.Module):
         first = next(iter(params.values()))
         if not first.is_cuda:
             raise _abi.ShotVaeError("VariationalAutoEncoder must be on a CUDA device (call .cuda()); no CPU path exists")
-        net = Net(named_params=params, named_buffers=bufs, device=first.device, **self._cfg)
+        net = Net(named_params=params, named_buffers=bufs, device=first.device, precision=self.precision, **self._cfg)
         for k, p in params.items():
             p.data = net.p(k)
             p.grad = None
@@ -192,7 +196,8 @@ class VariationalAutoEncoder(nn.Module):
         self.__dict__["_plist"] = list(params.values())
 
     def _ensure_bound(self):
-        if self._net is None or self._first.data_ptr() != self._net.p(self._first_name).data_ptr():
+        if self._net is None or self._first.data_ptr() != self._net.p(self._first_name).data_ptr() or \
+                self._net.precision != self.precision:
             self._bind()
 
     def _pack_if_needed(self):

@@ -82,6 +82,14 @@ _PROTOS = {
     "sv_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwdTerm), i32, vp, vp, vp, f32, i64, i32, i32, i32, vp]),
     "sv_bn_running_update": (C.c_int, [C.POINTER(vp), C.POINTER(vp), i32, f32, f32, i32, vp, vp, vp, vp]),
     "sv_colsum_bf16": (C.c_int, [vp, vp, i64, i32, i32, vp]),
+    "sv_pad_channels_f32": (C.c_int, [vp, vp, i64, i32, i32, vp]),
+    "sv_colsum_f32": (C.c_int, [vp, vp, i64, i32, i32, vp]),
+    "sv_pack_image_f32": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "sv_bn_act_fwd_f32": (C.c_int, [vp, vp, vp, vp, f32, i64, i32, i32, vp]),
+    "sv_bn_finalize_act_fwd_f32": (C.c_int, [vp, vp, vp, vp, vp, f32, f32, f32, i64, i32, i32, vp, vp, vp, vp, vp]),
+    "sv_bn_act_gap_fwd_f32": (C.c_int, [vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]),
+    "sv_bn_bwd_reduce_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, f32, f32, i64, i32, i32, i32, vp, vp, vp]),
+    "sv_bn_bwd_apply_f32": (C.c_int, [C.POINTER(BnBwdTerm), i32, vp, vp, vp, f32, i64, i32, i32, i32, vp]),
     "sv_linear_fwd": (C.c_int, [vp, i32, vp, i32, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp]),
     "sv_linear_bwd_input": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
     "sv_linear_bwd_weight": (C.c_int, [vp, vp, i32, vp, i32, vp, i32, i32, vp, i32, i32, i32, vp]),

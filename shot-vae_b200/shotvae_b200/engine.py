@@ -174,8 +174,15 @@ class TrainStep:
         for g, img in ((0, self.img_l), (1, self.img_u)):
             r = slice(g * B, (g + 1) * B)
             t = self.terms[3 * g:]
-            check(lib.sv_elbo_rec_fwd_bwd(ptr(img), ptr(rec[r]), 1, B, ch, 32 * 32, bce, float(self.h["x_sigma"]), ptr(self.coef),
-                                          ptr(t), ptr(g_rec[r]), cp, None, st))
+            if net.f32:
+                # FP32 mode: fp32 gradient in the layout of x_hat (NHWC, `ch` channels), then padded to the decoder's 16
+                g32 = ctx.t("g.rec.f32", (2 * B, 32, 32, ch), torch.float32)
+                check(lib.sv_elbo_rec_fwd_bwd(ptr(img), ptr(rec[r]), 1, B, ch, 32 * 32, bce, float(self.h["x_sigma"]), ptr(self.coef),
+                                              ptr(t), None, 0, ptr(g32[r]), st))
+                check(lib.sv_pad_channels_f32(ptr(g32[r]), ptr(g_rec[r]), B * 32 * 32, ch, cp, st))
+            else:
+                check(lib.sv_elbo_rec_fwd_bwd(ptr(img), ptr(rec[r]), 1, B, ch, 32 * 32, bce, float(self.h["x_sigma"]), ptr(self.coef),
+                                              ptr(t), ptr(g_rec[r]), cp, None, st))
             check(lib.sv_elbo_kl_fwd(ptr(mu[r]), ptr(ls[r]), ptr(la[r]), B, D, nd, ptr(t), st))
             check(lib.sv_elbo_kl_bwd(ptr(mu[r]), ptr(ls[r]), ptr(la[r]), ptr(t), ptr(self.coef[1:]), 0, B, D, nd, ptr(g_mu[r]),
                                      ptr(g_ls[r]), ptr(g_la[r]), 0, st))
@@ -221,8 +228,8 @@ class TrainStep:
         self._noise()
         # ---- forward of [P1 | P3]
         xA = A.t("x_img", (2 * B, 32, 32, cp))
-        check(lib.sv_pack_image(ptr(self.img_l), ptr(xA[:B]), B, ch, 32 * 32, cp, st))
-        check(lib.sv_pack_image(ptr(self.img_u), ptr(xA[B:]), B, ch, 32 * 32, cp, st))
+        check(net.fn("sv_pack_image")(ptr(self.img_l), ptr(xA[:B]), B, ch, 32 * 32, cp, st))
+        check(net.fn("sv_pack_image")(ptr(self.img_u), ptr(xA[B:]), B, ch, 32 * 32, cp, st))
         feat = net.encoder_fwd(A, xA)
         mu, ls, la = net.heads_fwd(A, feat)
         # From here two independent chains run until part 1: (a) sample -> decoder forward -> ELBO terms -> decoder
@@ -256,12 +263,19 @@ class TrainStep:
         if not self.m2:
             # ---- label smoothing (P1 -> P2 inputs) and optimal-interpolation mixup (P3 -> P4 inputs)
             xB = Bc.t("x_img", (2 * B, 32, 32, cp))
+            # (FP32 mode: the mixed images are written as fp32 NCHW and then laid out NHWC like any input batch)
+            xm = Bc.t("x_mix.f32", (2 * B, ch, 32, 32), torch.float32) if net.f32 else None
+            o32 = (lambda r: ptr(xm[r])) if net.f32 else (lambda r: None)
+            o16 = (lambda r: None) if net.f32 else (lambda r: ptr(xB[r]))
+            lo, hi = slice(0, B), slice(B, 2 * B)
             check(lib.sv_mixup_lerp(ptr(self.img_l), ptr(mu[:B]), ptr(ls[:B]), ptr(la[:B]), ptr(self.idx_l), ptr(self.lam), B, ch,
-                                    32 * 32, D, nd, None, ptr(xB[:B]), cp, ptr(self.s_mu), ptr(self.s_sig), ptr(self.s_alpha), st))
+                                    32 * 32, D, nd, o32(lo), o16(lo), cp, ptr(self.s_mu), ptr(self.s_sig), ptr(self.s_alpha), st))
             if self.h["om"]:
                 check(lib.sv_pairwise_kl_second_nearest(ptr(mu[B:]), ptr(ls[B:]), B, D, ptr(self.idx_u), None, st))
             check(lib.sv_mixup_lerp(ptr(self.img_u), ptr(mu[B:]), ptr(ls[B:]), ptr(la[B:]), ptr(self.idx_u), ptr(self.lam[2:]), B, ch,
-                                    32 * 32, D, nd, None, ptr(xB[B:]), cp, ptr(self.m_mu), ptr(self.m_sig), ptr(self.m_alpha), st))
+                                    32 * 32, D, nd, o32(hi), o16(hi), cp, ptr(self.m_mu), ptr(self.m_sig), ptr(self.m_alpha), st))
+            if net.f32:
+                check(lib.sv_pack_image_f32(ptr(xm), ptr(xB), 2 * B, ch, 32 * 32, cp, st))
             # ---- forward of [P2 | P4]
             featB = net.encoder_fwd(Bc, xB)
             mu2, ls2, la2 = net.heads_fwd(Bc, featB)

@@ -139,7 +139,10 @@ class Ctx:
         self.bn = OrderedDict()   # bn name -> dict(mean, var, count, ...)
         self.tape = []
 
-    def t(self, name, shape, dtype=torch.bfloat16):
+    def t(self, name, shape, dtype=None):
+        """dtype None = the network's activation type (bf16; fp32 in the parity-grade mode)"""
+        if dtype is None:
+            dtype = self.net.adt
         b = self.bufs.get(name)
         if b is None:
             if self.parent is not None:
@@ -183,7 +186,14 @@ class Ctx:
 
 # ------------------------------------------------------------------------------------ the net
 class Net:
-    def __init__(self, encoder_name, nd, ldc, in_ch, named_params, named_buffers, device, temperature=0.67, impl=0):
+    def __init__(self, encoder_name, nd, ldc, in_ch, named_params, named_buffers, device, temperature=0.67, impl=0,
+                 precision="bf16"):
+        """precision: "bf16" = production (bf16 NHWC activations and conv operands on the tcgen05 kernels, fp32 accumulation /
+        statistics / losses / optimizer); "fp32" = parity-grade mode (every activation tensor and conv operand fp32, the
+        FP32 kernels of csrc/igemm_f32.cu and the `_f32` elementwise entry points; same launch sequence)."""
+        assert precision in ("bf16", "fp32"), precision
+        self.precision, self.f32 = precision, precision == "fp32"
+        self.adt = torch.float32 if self.f32 else torch.bfloat16
         self.encoder_name, self.nd, self.ldc, self.in_ch = encoder_name, nd, ldc, in_ch
         self.device = torch.device(device)
         self.topo = encoder_topology(encoder_name)
@@ -221,6 +231,12 @@ class Net:
         self.timing = None        # bench instrumentation: list of (kind, key, flops, ev0, ev1, algorithmic bytes) when enabled
         self._build_packs()
 
+    def fn(self, name):
+        """the C-ABI entry point for this network's activation type: `name` (bf16) or its `_f32` twin"""
+        if not self.f32:
+            return getattr(lib, name)
+        return getattr(lib, {"sv_colsum_bf16": "sv_colsum_f32"}.get(name, name + "_f32"))
+
     # ---- views
     def p(self, name):
         o, n, shp = self.poff[name]
@@ -243,9 +259,9 @@ class Net:
         is asked whether the halo-tile tcgen05 kernel covers the problem; if so the weights are packed in
         its 8-channel-plane layout."""
         T = len(taps)
-        dst = torch.zeros(T, N, C, dtype=torch.bfloat16, device=self.device)
-        layout = 0
-        if grid is not None and self.impl in (0, 3) and os.environ.get("SHOTVAE_HALO", "1") != "0":      # (A/B switch: 0 = per-tap TMA kernel everywhere)
+        dst = torch.zeros(T, N, C, dtype=self.adt, device=self.device)
+        layout = 2 if self.f32 else 0       # 2: fp32 [T][N][C] operands of the FP32 kernels
+        if not self.f32 and grid is not None and self.impl in (0, 3) and os.environ.get("SHOTVAE_HALO", "1") != "0":      # (A/B switch: 0 = per-tap TMA kernel everywhere)
             a = IgemmArgs()
             a.A = a.Wt = a.out_bf16 = ptr(dst)
             a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = 128, grid[0], grid[1], C, grid[0], grid[1], N, T
@@ -326,6 +342,8 @@ class Net:
         BatchNorm `rec` (input y) into `stats` ([2][G][N]: dbeta block, dgamma block); returns False (nothing launched, nothing
         changed) when the kernel that runs this shape has no such epilogue, so that the caller can fall back to
         sv_bn_bwd_reduce."""
+        if self.f32 and bnb is not None:
+            return False                     # the FP32 kernel has no fused-statistics epilogue: the caller runs sv_bn_bwd_reduce
         a = ctx.args.get(key)
         if a is None:
             pk = self.packs[pack]
@@ -344,6 +362,8 @@ class Net:
         # operand pointers are refreshed on every call (callers may hand in different tensors)
         a.A, a.out_bf16, a.out_f32, a.residual, a.bias, a.stats = ptr(A), ptr(out), ptr(outf), ptr(res), ptr(bias), ptr(stats)
         a.impl = 3 if a.w_layout == 1 else (self.impl if self.impl != 3 else 0)
+        if self.f32:                         # every tensor is fp32: the output goes through out_f32 (row length N unless n_valid)
+            a.out_bf16, a.out_f32, a.impl = None, ptr(out if out is not None else outf), 4
         if bnb is not None:
             rec = bnb["rec"]
             a.bn_y, a.bn_scale, a.bn_shift, a.bn_mean, a.bn_var = ptr(bnb["y"]), ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"])
@@ -390,6 +410,8 @@ class Net:
             bmn = 128 if N % 128 == 0 else 64 if N % 64 == 0 else 32 if N % 32 == 0 else 16
             tiles = ((T * Cc + 127) // 128) * ((N + bmn - 1) // bmn)
             M = NB * OH * OW
+            if self.f32:                     # 64 x 64 output tiles of the FP32 kernel
+                tiles = ((T * Cc + 63) // 64) * ((N + 63) // 64)
             splits = max(1, min((296 + tiles - 1) // tiles, max(1, M // 256)))
             while splits > 1 and splits * N * T * Cc > self.wg_ws.numel():
                 splits -= 1
@@ -399,9 +421,9 @@ class Net:
             a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = NB, H, W, Cc, OH, OW, N, T
             a.in_stride, a.splits = in_stride, splits
             a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
-            a.impl = 1 if self.impl == 1 else 0
+            a.impl = 4 if self.f32 else (1 if self.impl == 1 else 0)
             a.A, a.Gr = ptr(A), ptr(Gr)
-            tc_splits = lib.sv_igemm_wgrad_splits(byref(a))     # > 0: the tcgen05 kernel runs it, one slice per CTA
+            tc_splits = 0 if self.f32 else lib.sv_igemm_wgrad_splits(byref(a))     # > 0: the tcgen05 kernel runs it, one slice per CTA
             if tc_splits > 0:
                 splits = a.splits = tc_splits
                 assert splits * N * T * Cc <= self.wg_ws.numel(), "wgrad workspace too small for %s" % key
@@ -467,7 +489,7 @@ class Net:
             self._bn_eval_coeffs(bn_name, rec)
             self._bn_act(ctx, y, a, rec, slope, count)
             return rec
-        self._timed("bn_fwd_act", key, 4 * y.numel(), lambda: check(lib.sv_bn_finalize_act_fwd(
+        self._timed("bn_fwd_act", key, 4 * y.numel(), lambda: check(self.fn("sv_bn_finalize_act_fwd")(
             ptr(y), ptr(a), ptr(stats), ptr(self.p(bn_name + ".weight")), ptr(self.p(bn_name + ".bias")), float(count), BN_EPS,
             float(slope), count, G, Cc, ptr(rec["mean"]), ptr(rec["var"]), ptr(rec["scale"]), ptr(rec["shift"]), _abi.stream())))
         ctx.bn[bn_name] = rec
@@ -484,7 +506,7 @@ class Net:
             rec[k][:, :Cr] = v
 
     def _bn_act(self, ctx, y, a, rec, slope, rows_per_group):
-        check(lib.sv_bn_act_fwd(ptr(y), ptr(a), ptr(rec["scale"]), ptr(rec["shift"]), float(slope), rows_per_group, ctx.G,
+        check(self.fn("sv_bn_act_fwd")(ptr(y), ptr(a), ptr(rec["scale"]), ptr(rec["shift"]), float(slope), rows_per_group, ctx.G,
                                 rec["C"], _abi.stream()))
 
     def _bn_bwd_stats(self, ctx, key, i, Cc):
@@ -504,7 +526,7 @@ class Net:
             db, dg = self._bn_bwd_stats(ctx, key, i, Cc)
             gb = 2 * t["g_a"].numel() if t.get("g_a") is not None else 0
             if not t.get("fused"):           # (fused: the input-gradient conv's epilogue has already accumulated db / dg)
-                self._timed("bn_bwd_reduce", key, gb + 2 * y.numel(), lambda: check(lib.sv_bn_bwd_reduce(
+                self._timed("bn_bwd_reduce", key, gb + 2 * y.numel(), lambda: check(self.fn("sv_bn_bwd_reduce")(
                     ptr(t.get("g_a")), ptr(t.get("g_feat")), ptr(y), ptr(rec["scale"]), ptr(rec["shift"]), ptr(rec["mean"]), ptr(rec["var"]),
                     BN_EPS, float(t["slope"]), rows_per_group, HW, G, Cc, ptr(dg), ptr(db), s)))
             arr[i].g_a, arr[i].g_feat = ptr(t.get("g_a")), ptr(t.get("g_feat"))
@@ -513,7 +535,7 @@ class Net:
             arr[i].grad_gamma, arr[i].grad_beta = ptr(self.g(rec["name"] + ".weight")), ptr(self.g(rec["name"] + ".bias"))
             arr[i].slope, arr[i].c_real = float(t["slope"]), Cc
         nb = 2 * y.numel() * (2 + sum(1 for t in terms if t.get("g_a") is not None) + (1 if addend is not None else 0))
-        self._timed("bn_bwd_apply", key, nb, lambda: check(lib.sv_bn_bwd_apply(arr, len(terms), ptr(y), ptr(addend), ptr(g_y), BN_EPS,
+        self._timed("bn_bwd_apply", key, nb, lambda: check(self.fn("sv_bn_bwd_apply")(arr, len(terms), ptr(y), ptr(addend), ptr(g_y), BN_EPS,
                                                                                rows_per_group, HW, G, Cc, s)))
 
     # ---- encoder -------------------------------------------------------------------------------
@@ -556,7 +578,7 @@ class Net:
         feat = ctx.t("feat", (NB, Cf), torch.float32)
         ctx.enc_out = dict(h=h, H=H, bnT=bnT)
         if not self.dry:
-            check(lib.sv_bn_act_gap_fwd(ptr(h), ptr(feat), ptr(bnT["scale"]), ptr(bnT["shift"]), float(slope), NB, H * H, Cf, B,
+            check(self.fn("sv_bn_act_gap_fwd")(ptr(h), ptr(feat), ptr(bnT["scale"]), ptr(bnT["shift"]), float(slope), NB, H * H, Cf, B,
                                         _abi.stream()))
         return feat
 
@@ -685,8 +707,8 @@ class Net:
         cin_p = pad16(self.in_ch)
         self._wgrad(ctx, "conv0.w", ctx.x_img, g_h, conv_taps(3, 1), NB, 32, 32, cin_p, 32, 32, f0, 1,
                     "feature_extractor.encoder.pre_process.conv0.weight", f0, self.in_ch, self.in_ch * 9, 9, 1)
-        check(lib.sv_colsum_bf16(ptr(g_h), ptr(self.g("feature_extractor.encoder.pre_process.conv0.bias")), NB * 32 * 32, f0, f0,
-                                 _abi.stream()))
+        check(self.fn("sv_colsum_bf16")(ptr(g_h), ptr(self.g("feature_extractor.encoder.pre_process.conv0.bias")), NB * 32 * 32, f0, f0,
+                                        _abi.stream()))
 
     def _dgrad(self, ctx, key, g_out, g_in, NB, Ho, Hin, stride, bnb=None):
         """input gradient of a conv by output-parity phases (stride 1: a single phase).  bnb (stride 1 only): fuse the
@@ -785,7 +807,7 @@ class Net:
         y = ctx.t("d0.y", (NB, 1, 1, c0))
         st = ctx.z("d0.st", G * 2 * c0)
         check(lib.sv_linear_fwd(ptr(latent), self.latent, ptr(self.p("feature_reconstructor.decoder.0.weight")), c0, 1, None,
-                                None, ptr(y), c0, ptr(st), B, NB, c0, self.latent, s))
+                                ptr(y) if self.f32 else None, None if self.f32 else ptr(y), c0, ptr(st), B, NB, c0, self.latent, s))
         ctx.dec = []
         ctx.dec_latent = latent
         cin, hin = c0, 1
@@ -831,10 +853,11 @@ class Net:
             g, cout, cout_p = g_y, cin, cin
         c0 = DEC_CHANNELS[0]
         w0 = "feature_reconstructor.decoder.0.weight"
-        check(lib.sv_linear_bwd_weight(None, ptr(g), c0, ptr(ctx.dec_latent), self.latent, ptr(self.g(w0)), c0, 1, None, NB, c0,
+        g32, g16 = (ptr(g), None) if self.f32 else (None, ptr(g))
+        check(lib.sv_linear_bwd_weight(g32, g16, c0, ptr(ctx.dec_latent), self.latent, ptr(self.g(w0)), c0, 1, None, NB, c0,
                                        self.latent, s))
         g_lat = ctx.t("g.latent", (NB, self.latent), torch.float32)
-        check(lib.sv_linear_bwd_input(None, ptr(g), c0, ptr(self.p(w0)), c0, 1, ptr(g_lat), self.latent, 0, NB, c0, self.latent, s))
+        check(lib.sv_linear_bwd_input(g32, g16, c0, ptr(self.p(w0)), c0, 1, ptr(g_lat), self.latent, 0, NB, c0, self.latent, s))
         return g_lat
 
     # ---- BatchNorm running statistics ----------------------------------------------------------
