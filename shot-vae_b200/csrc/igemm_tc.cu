@@ -44,6 +44,7 @@ struct TcParams {
   int m_tiles, n_tiles, BN, KB;
   int rows_per_group, groups;
   int stages;
+  int in_stride;             // 1, or 2: the A boxes sample every second pixel (tensor-map element strides)
   int swizzle_bytes;         // 64 or 128
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
@@ -197,7 +198,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           if (do_a) {
             mbar_expect_tx(&full_bar[stage], a_bytes);
-            tma_load_4d(sa, &tmA, &full_bar[stage], cb * p.KB, (int)p.dx[t], h0 + (int)p.dy[t], img0);
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * p.KB, (int)p.dx[t], p.in_stride * h0 + (int)p.dy[t], img0);
           }
           if (do_b) {
             mbar_expect_tx(&full_bar[stage], b_bytes);
@@ -449,8 +450,11 @@ static int pick_bn(int N) {
 bool igemm_fprop_tc_supported(const IgemmParams& p) {
   TileGeom g;
   if (p.w_layout != 0) return false;
-  if (p.in_stride != 1 || p.H != p.OH || p.W != p.OW) return false;
+  // stride 2 (the first conv / projection shortcut of a resolution block): same kernel, the tensor map of A traverses H and
+  // W with element stride 2, so a box of (2 Wt) x (2 Ht) input pixels lands in shared memory as the Wt x Ht pixels the tile needs
+  if (!(p.in_stride == 1 || p.in_stride == 2) || p.H != p.OH * p.in_stride || p.W != p.OW * p.in_stride) return false;
   if (!tile_geom(p.OH, p.OW, &g)) return false;
+  if (g.Wt * p.in_stride > 256 || g.Ht * p.in_stride > 256) return false;
   if (p.C % 32 != 0 || p.N % 16 != 0) return false;
   if (pick_bn(p.N) == 0) return false;
   if (p.out == nullptr || p.outf != nullptr) return false;
@@ -494,6 +498,7 @@ static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtenso
   if (stages > 8) stages = 8;
   if (stages < 4) { sv_set_error("igemm_fprop_tc: tile too large (the producers' parity protocol needs >= 4 stages)"); return SV_ERR_UNSUPPORTED; }
   q.stages = stages;
+  q.in_stride = p.in_stride;
   memcpy(q.dy, p.dy, SV_MAX_TAPS);
   memcpy(q.dx, p.dx, SV_MAX_TAPS);
 
@@ -501,8 +506,9 @@ static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtenso
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.NB};
     cuuint64_t strides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)q.KB, (cuuint32_t)g.Wt, (cuuint32_t)g.Ht, (cuuint32_t)g.Nt};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    const cuuint32_t is = (cuuint32_t)p.in_stride;    // box extents are in tensor elements: ceil(box / stride) pixels are loaded
+    cuuint32_t box[4] = {(cuuint32_t)q.KB, (cuuint32_t)g.Wt * is, (cuuint32_t)g.Ht * is, (cuuint32_t)g.Nt};
+    cuuint32_t es[4] = {1, is, is, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(p.A), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sv_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return SV_ERR_CUDA; }

@@ -38,6 +38,7 @@ struct WtcParams {
   int Nt, Ht, tiles_h;       // box geometry (images, rows per block; blocks per image column)
   int cb, c_blocks, boxes;   // channels per MMA (N of the instruction), C / cb, ceil(cb / 64)
   int pairs, ppu, units_per_nt, splits;
+  int in_stride;             // 1, or 2: the activation boxes sample every second pixel (tensor-map element strides)
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
 };
@@ -163,7 +164,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
           const int pair = pair0 + pr, t = pair / p.c_blocks, cblk = pair - t * p.c_blocks;
           mbar_wait(&a_empty[ps], (uint32_t)(((ai >> 1) & 1) ^ 1));
           mbar_expect_tx(&a_full[ps], BOX_BYTES);
-          tma_load_4d(a_base + ps * a_stage + pbx * BOX_BYTES, &tmA, &a_full[ps], cblk * p.cb + 64 * pbx, (int)p.dx[t], h0 + (int)p.dy[t], img0);
+          tma_load_4d(a_base + ps * a_stage + pbx * BOX_BYTES, &tmA, &a_full[ps], cblk * p.cb + 64 * pbx, (int)p.dx[t], p.in_stride * h0 + (int)p.dy[t], img0);
         }
       }
     }
@@ -263,17 +264,20 @@ int pick_cb(int C) {
 }
 
 bool geometry(const WgradParams& p, WtcParams& q) {
-  if (p.W <= 0 || p.W > BLK || BLK % p.W) return false;
-  const int rows = BLK / p.W;
-  if (p.H >= rows) {
-    if (p.H % rows) return false;
+  // pixel blocks tile the OUTPUT grid (the rows of G); the activation box of a block covers in_stride x as many input pixels
+  if (p.OW <= 0 || p.OW > BLK || BLK % p.OW) return false;
+  const int rows = BLK / p.OW;
+  if (p.OH >= rows) {
+    if (p.OH % rows) return false;
     q.Ht = rows; q.Nt = 1;
   } else {
-    if (rows % p.H) return false;
-    q.Ht = p.H; q.Nt = rows / p.H;
+    if (rows % p.OH) return false;
+    q.Ht = p.OH; q.Nt = rows / p.OH;
     if (p.NB % q.Nt) return false;
   }
-  q.tiles_h = p.H / q.Ht;
+  if (p.OW * p.in_stride > 256 || q.Ht * p.in_stride > 256) return false;
+  q.in_stride = p.in_stride;
+  q.tiles_h = p.OH / q.Ht;
   q.PB = p.M / BLK;
   q.N = p.N; q.C = p.C; q.T = p.T;
   q.cb = pick_cb(p.C);
@@ -296,7 +300,7 @@ bool geometry(const WgradParams& p, WtcParams& q) {
 }  // namespace
 
 bool wgrad_tc_supported(const WgradParams& p) {
-  if (p.in_stride != 1 || p.H != p.OH || p.W != p.OW) return false;
+  if (!(p.in_stride == 1 || p.in_stride == 2) || p.H != p.OH * p.in_stride || p.W != p.OW * p.in_stride) return false;
   if (p.C < 64 || p.N < 64 || p.C % 16 || p.N % 16) return false;       // narrow layers: the halo-tile kernel
   if (p.M % BLK) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.Gr) & 15) || (reinterpret_cast<uintptr_t>(p.partial) & 15)) return false;
@@ -319,11 +323,11 @@ int wgrad_tc(const WgradParams& p, cudaStream_t st) {
   EncodeTiledFn encode = get_encode();
   if (!encode) { sv_set_error("cuTensorMapEncodeTiled unavailable"); return SV_ERR_UNSUPPORTED; }
   CUtensorMap tmG, tmA;
-  cuuint32_t box[4] = {64, (cuuint32_t)p.W, (cuuint32_t)q.Ht, (cuuint32_t)q.Nt};
+  cuuint32_t box[4] = {64, (cuuint32_t)p.OW, (cuuint32_t)q.Ht, (cuuint32_t)q.Nt};
   cuuint32_t es[4] = {1, 1, 1, 1};
   {
-    cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.NB};
-    cuuint64_t strides[3] = {(cuuint64_t)p.N * 2, (cuuint64_t)p.W * p.N * 2, (cuuint64_t)p.H * p.W * p.N * 2};
+    cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.NB};
+    cuuint64_t strides[3] = {(cuuint64_t)p.N * 2, (cuuint64_t)p.OW * p.N * 2, (cuuint64_t)p.OH * p.OW * p.N * 2};
     CUresult r = encode(&tmG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(p.Gr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sv_set_error("cuTensorMapEncodeTiled(G) failed: %d", (int)r); return SV_ERR_CUDA; }
@@ -331,7 +335,10 @@ int wgrad_tc(const WgradParams& p, cudaStream_t st) {
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.NB};
     cuuint64_t strides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(p.A), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint32_t is = (cuuint32_t)p.in_stride;    // box extents are in tensor elements: ceil(box / stride) pixels are loaded
+    cuuint32_t abox[4] = {64, (cuuint32_t)p.OW * is, (cuuint32_t)q.Ht * is, (cuuint32_t)q.Nt};
+    cuuint32_t aes[4] = {1, is, is, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(p.A), dims, strides, abox, aes, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sv_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return SV_ERR_CUDA; }
   }

@@ -309,3 +309,37 @@ def test_fp32_engine_c2_b128_matches_reference_golden():
             scale = moved / gs["numel"] ** 0.5
             for p, v in zip(sample_positions(t.numel()), gs["samples"]):
                 assert abs(float(t[p]) - v) < 10 * GRAD_TOL * scale + 1e-6 * abs(v), (k, p, float(t[p]), v)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_c4_wrn28x10_engine_step_matches_oracle(precision):
+    """C4 (WideResNet-28-10: 160 / 320 / 640 channels, the TMA-fed tcgen05 kernels for wide layers) -- one full fused step
+    (4 forwards, 2 backwards, SGD) against the oracle's step.  bf16: loss terms at 1e-3 and the same update gates as the other
+    bf16 engine tests (same-precision control documented in test_gpu_step.py); fp32 mode: north-star bounds end to end."""
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    net, nd, batch, epoch = "wideresnet-28-10", 10, 8, 100
+    hyper = O.default_hyper("Cifar10")
+    st, ost, (il, ll, iu, lu), outs, logs = _oracle_step_with_sgd(net, nd, batch, epoch, hyper, 5, 11)
+    model = build_model(net, nd, st)
+    model.precision = precision
+    model.train()
+    ts = TrainStep(model, batch, hyper={k: v for k, v in hyper.items() if k != "temperature"}, use_graph=False, device_noise=False)
+    ts.set_epoch(epoch)
+    got = ts.step(il, ll, iu, lu, draws=_feed(ts, logs[0], False))
+    want = outs[0]
+    _report("terms_engine_c4_b8_" + precision, {k: dict(got=got[k], want=want[k]) for k in want if k in got and isinstance(want[k], float)})
+    _check_terms(got, want, ("rec_l", "klc_l", "rec_u", "klc_u"))
+    _check_terms(got, want, ("disc_post_l", "disc_post_u", "kl_inference"), TERM_TOL if precision == "fp32" else 1e-2)
+    sd = model.state_dict()
+    upd = {k: sd[k].float().cpu() - st[k].float() for k in O.param_names(ost)}
+    wupd = {k: ost[k].detach().float() - st[k].float() for k in O.param_names(ost)}
+    errs = grad_errors(upd, wupd)
+    _report("update_rel_l2_engine_c4_b8_" + precision, errs)
+    if precision == "fp32":
+        for grp in ("encoder", "decoder", "heads", "all"):
+            assert errs[grp] < GRAD_TOL, (grp, errs)
+    else:
+        assert errs["decoder"] < 0.15 and errs["heads"] < 0.15 and errs["encoder"] < 0.65, errs
+    rs = max(rel(sd[k], ost[k]) for k in ost if k.endswith("running_mean") or k.endswith("running_var"))
+    assert rs < (1e-3 if precision == "fp32" else 3e-2), rs
