@@ -36,7 +36,8 @@ struct WgParams {
   const bf16* A;
   const bf16* G;
   float* partial;            // [ctas][N][T*C]  (ctas = splits of sv_wgrad_reduce)
-  int NB, H, W, C, N, T;
+  int NB, H, W, C, N, T;     // N = output channels of THIS launch (a power-of-two slice of the layer's Ntot)
+  int Ntot, n_off;           // row pitch of G / of the partial slices, first channel of the slice
   int P, R, Rg;
   int tiles_per_img, items;
   int groups, taps_per_group, ctas_per_group;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
   if (warp >= 4 && warp < 8) {
     // ===================================== producers ========================================
     const int ptid = tid - 128;
-    const size_t a_row = (size_t)p.W * p.C, g_row = (size_t)p.W * p.N;
+    const size_t a_row = (size_t)p.W * p.C, g_row = (size_t)p.W * p.Ntot;
     int stage = 0;
     uint32_t phase = 0;
     int img = cta / p.tiles_per_img, j = cta - img * p.tiles_per_img;
@@ -161,12 +162,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
       mbar_wait(&empty_bar[stage], phase ^ 1);
       const uint32_t sbase = smem_u32(smem) + (uint32_t)stage * p.stage_bytes + PAD_SLOTS * 16;
       {   // output-gradient tile: rows yg0 .. yg0+Rg-1 (padded), i.e. image rows yg0-1 ..
-        const bf16* img_base = p.G + (size_t)img * p.H * g_row;
+        const bf16* img_base = p.G + (size_t)img * p.H * g_row + p.n_off;
         for (int ch = ptid; ch < p.g_chunks_per_row; ch += PRODUCERS) {
           const int slot = ch >> p.g_planes_log2, pl = ch & (p.g_planes - 1);
           uint32_t dst = sbase + (uint32_t)pl * p.g_plane_bytes + (uint32_t)(1 + slot) * 16;
           int yu = yg0 - 1;
-          const bf16* src = img_base + (size_t)ch * 8 + (ptrdiff_t)yu * (ptrdiff_t)g_row;
+          const bf16* src = img_base + (size_t)slot * p.Ntot + (size_t)pl * 8 + (ptrdiff_t)yu * (ptrdiff_t)g_row;
 #pragma unroll 4
           for (int r = 0; r < p.Rg; ++r, ++yu, dst += (uint32_t)p.P * 16, src += g_row) {
             const bool ok = yu >= 0 && yu < p.H;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_halo_kernel(const WgParam
     // 32q .. 32q+15 (MEASURED, tools/m64_probe.cu), i.e. the low half of every warp's lane quarter.
     const int n = (p.mma_m == 64) ? (lane < 16 ? warp * 16 + lane : p.N) : warp * 32 + lane;
     const int TC = p.T * p.C;
-    float* dst = p.partial + ((size_t)cta * p.N + n) * TC + (size_t)t0 * p.C;
+    float* dst = p.partial + ((size_t)cta * p.Ntot + p.n_off + n) * TC + (size_t)t0 * p.C;
     const int ncols = ntaps * p.C;
     const bool has_items = cta < p.items;
     for (int c0 = 0; c0 < ncols; c0 += 16) {
@@ -294,7 +295,9 @@ bool wgrad_halo_supported(const WgradParams& p) {
   if (p.in_stride != 1 || p.H != p.OH || p.W != p.OW) return false;
   if (!((p.W == 32 || p.W == 16 || p.W == 8) && p.H >= 8 && p.H <= 32)) return false;
   if (!(p.C == 16 || p.C == 32 || p.C == 64 || p.C == 128)) return false;
-  if (!(p.N == 16 || p.N == 32 || p.N == 64 || p.N == 128)) return false;
+  // output channels: a power of two up to 128, or a sum of such slices (WRN-28-10's 16 -> 160 stem convs: 128 + 32),
+  // one launch per slice over the same activation tiles
+  if (p.N % 16 != 0 || p.N > 256) return false;
   for (int t = 0; t < p.T; ++t)
     if (p.dy[t] < -1 || p.dy[t] > 1 || p.dx[t] < -1 || p.dx[t] > 1) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.Gr) & 15) || (reinterpret_cast<uintptr_t>(p.partial) & 15))
@@ -313,11 +316,28 @@ int wgrad_halo_splits(const WgradParams& p) {
   return ctas;
 }
 
+static int wgrad_halo_slice(const WgradParams& p, int n_off, int n_slice, cudaStream_t st);
+
 int wgrad_halo(const WgradParams& p, cudaStream_t st) {
+  int n_off = 0;
+  while (n_off < p.N) {
+    int n_slice = 128;
+    while (n_slice > p.N - n_off) n_slice >>= 1;
+    const int rc = wgrad_halo_slice(p, n_off, n_slice, st);
+    if (rc != SV_OK) return rc;
+    n_off += n_slice;
+  }
+  return SV_OK;
+}
+
+static int wgrad_halo_slice(const WgradParams& p0, int n_off, int n_slice, cudaStream_t st) {
+  WgradParams p = p0;
+  p.N = n_slice;
   WgParams q;
   memset(&q, 0, sizeof(q));
   q.A = p.A; q.G = p.Gr; q.partial = p.partial;
   q.NB = p.NB; q.H = p.H; q.W = p.W; q.C = p.C; q.N = p.N; q.T = p.T;
+  q.Ntot = p0.N; q.n_off = n_off;
   q.P = p.W + 2;
   int R = (4 * q.P + BM) / q.P;
   if (R > p.H + 2) R = p.H + 2;

@@ -311,7 +311,9 @@ def wgrad(sv, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, grad, n_real, c_r
                                                            (64, 160, 16, 1, 1, 4, 1), (160, 320, 16, 1, 1, 2, 1),
                                                            # stride 2 on the TMA kernel (tensor-map element strides)
                                                            (64, 128, 16, 2, 3, 8, 1), (160, 320, 32, 2, 3, 4, 1), (320, 640, 16, 2, 1, 8, 1),
-                                                           (128, 256, 16, 2, 3, 2, 1)])
+                                                           (128, 256, 16, 2, 3, 2, 1),
+                                                           # halo-tile kernel, output channels in power-of-two slices (128 + 32, 64 + 32)
+                                                           (16, 160, 32, 1, 3, 4, 1), (16, 160, 32, 1, 1, 4, 1), (32, 96, 16, 1, 3, 4, 1)])
 def test_conv_wgrad_matches_autograd(sv, impl, cin, cout, H, stride, k, NB, splits):
     from shotvae_b200.plan import conv_taps
     torch.manual_seed(11 + cin + stride + k)
