@@ -304,7 +304,9 @@ def main():
     import torch.distributed as dist
     if world > 1:
         # NCCL's log (communicator ranks, NVLS / ring choice) goes to stderr: fd 1 is guarded, stdout stays the one JSON line
-        os.environ["NCCL_DEBUG"] = os.environ.get("SHOTVAE_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "INFO"))
+        # (forced: a box-level NCCL_DEBUG=WARN would hide the "comm ... nranks N" lines the driver checks; SHOTVAE_NCCL_DEBUG overrides)
+        os.environ["NCCL_DEBUG"] = os.environ.get("SHOTVAE_NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from shot_vae_model.vae import VariationalAutoEncoder
     from shotvae_b200.engine import TrainStep, default_hyper

@@ -57,6 +57,11 @@ class TrainStep:
         self.use_graph, self.device_noise = use_graph, device_noise
         self.skip_dead_decoders = skip_dead_decoders
         self.reducer = reducer
+        # Data parallel: one CUDA graph per backward segment, the NCCL calls issued between them from the host.
+        # SHOTVAE_DDP_GRAPH=single captures the all-reduces into ONE graph instead (works: NCCL supports stream capture) --
+        # MEASURED at 2 GPUs: 5.005 vs 5.021 ms/step, i.e. the host-side gaps are not what the 2 % data-parallel overhead is made
+        # of, and destroy_process_group() hung for minutes with the captured communicator still referenced -> opt-in only
+        self.ddp_single_graph = os.environ.get("SHOTVAE_DDP_GRAPH", "segments") == "single"
         # weight gradients overlap the dgrad / BatchNorm-backward chain on a second stream (SHOTVAE_SIDE=0 turns it off)
         if net.side is None and os.environ.get("SHOTVAE_SIDE", "1") != "0":
             net.side = torch.cuda.Stream(device=net.device)
@@ -359,13 +364,22 @@ class TrainStep:
             self._run_parts_eager()
         elif self.graph is None and self._calls >= 2:
             n0 = _abi.launch_count()
-            groups = [(0, 1, 2)] if self.reducer is None else [parts for parts, _ in self._ddp_plan()]
-            graphs = []
-            for parts in groups:
+            if self.reducer is not None and self.ddp_single_graph:
+                # data parallel, ONE graph: the bucket all-reduces are captured with the step (NCCL supports stream capture);
+                # they sit on the reducer's side stream, forked from / joined to the capture stream by bucket_ready / wait_all,
+                # so a replay has no host-side gaps between the backward segments
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._sequence(parts)
-                graphs.append(g)
+                    self._run_parts_eager()
+                graphs = [g]
+            else:
+                groups = [(0, 1, 2)] if self.reducer is None else [parts for parts, _ in self._ddp_plan()]
+                graphs = []
+                for parts in groups:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._sequence(parts)
+                    graphs.append(g)
             self.launches_per_step = _abi.launch_count() - n0
             self.graph = graphs
             self._replay()
@@ -381,7 +395,7 @@ class TrainStep:
         self.net.param_epoch += 1             # the fused SGD moved the FP32 masters: the drop-in forward must repack
 
     def _replay(self):
-        if self.reducer is None:
+        if self.reducer is None or len(self.graph) == 1:
             self.graph[0].replay()
             return
         for g, (_, bucket) in zip(self.graph, self._ddp_plan()):
