@@ -253,6 +253,16 @@ int sv_posterior_fwd_bwd(const float* la, const float* target, const int64_t* la
 /* inference-KL monitor (main_shot_vae.py:331-339): *out += sum alpha*(la - log smooth_onehot(label))/B */
 int sv_inference_kl(const float* la, const int64_t* label, int32_t B, int32_t nd, float* out, void* stream);
 
+/* ---- device-side noise and accumulator clears of the fused step -----------------------------------
+ * normal[0..n_normal) ~ N(0,1) (the eps of Sample.forward, vae.py:82-84) and uniform[0..n_uniform) ~ U[0,1) (the Gumbel
+ * uniforms, vae.py:69) from Philox4x32-10 at counter `offset`; `state` is a device struct {uint64 seed, uint64 offset,
+ * uint32 ticket, pad} (sv_sizeof_noise_state() = 32 bytes) whose offset the launch advances, so CUDA-graph replays draw
+ * fresh numbers.  Parity runs feed host-drawn noise (torch.randn / torch.rand in the reference's order) instead. */
+int sv_noise_fill(float* normal, int64_t n_normal, float* uniform, int64_t n_uniform, void* state, void* stream);
+int sv_sizeof_noise_state(void);
+/* graph-capturable memset (cudaMemsetAsync: a memset node, no kernel) for the per-step accumulators */
+int sv_fill_zero(void* dst, int64_t nbytes, void* stream);
+
 /* ---- mixup / label smoothing (mixup.py:5-41) ------------------------------------------------------
  * lam_dev = {lam, 1-lam} (fp32, device).  image fp32 NCHW [B, img_elems]; writes the mixed image as
  * fp32 NCHW (mixed_f32, optional) and as bf16 NHWC with `img_ld` channels (mixed_bf16, optional). */

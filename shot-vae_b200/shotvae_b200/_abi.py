@@ -103,6 +103,9 @@ _PROTOS = {
     "sv_posterior_fwd_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "sv_inference_kl": (C.c_int, [vp, vp, i32, i32, vp, vp]),
     "sv_mixup_lerp": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]),
+    "sv_noise_fill": (C.c_int, [vp, i64, vp, i64, vp, vp]),
+    "sv_sizeof_noise_state": (C.c_int, []),
+    "sv_fill_zero": (C.c_int, [vp, i64, vp]),
     "sv_pairwise_kl_second_nearest": (C.c_int, [vp, vp, i32, i32, vp, vp, vp]),
     "sv_sgd_step": (C.c_int, [vp, vp, vp, vp, i64, vp]),
     "sv_pairwise_dist": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),

@@ -80,6 +80,13 @@ class TrainStep:
         self.coef = z(16)
         self.sgd_hyper = z(8)
         self.terms = z(16)
+        # device noise (sv_noise_fill): {seed, offset, ticket, pad}; the seed follows torch's CUDA seed (reading it consumes no
+        # host RNG draw, so the reference's randperm / beta sequence is untouched) and the rank, streams of different
+        # TrainStep objects start 2^40 counters apart
+        TrainStep._instances = getattr(TrainStep, "_instances", 0) + 1
+        rank = 0 if reducer is None else int(torch.distributed.get_rank())
+        seed = (int(torch.cuda.initial_seed()) * 0x9E3779B97F4A7C15 + rank * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+        self.noise_state = torch.tensor([seed, TrainStep._instances << 40, 0, 0], dtype=i64, device=dev)
         self.kl_sum = z(1)           # sum of the per-step inference-KL monitor since it was last cleared (Train/KL_Inference, :331-339,376)
         self.kl_count = 0
         # mixup targets
@@ -192,12 +199,13 @@ class TrainStep:
             check(lib.sv_elbo_kl_bwd(ptr(mu[r]), ptr(ls[r]), ptr(la[r]), ptr(t), ptr(self.coef[1:]), 0, B, D, nd, ptr(g_mu[r]),
                                      ptr(g_ls[r]), ptr(g_la[r]), 0, st))
         check(lib.sv_inference_kl(ptr(la[B:]), ptr(self.label_u), B, nd, ptr(self.terms[10:]), st))
+        check(lib.sv_inference_kl(ptr(la[B:]), ptr(self.label_u), B, nd, ptr(self.kl_sum), st))      # epoch accumulator (+=): no per-step host sync
         return g_rec, g_mu, g_ls, g_la
 
     def _noise(self):
         if self.device_noise:
-            self.eps.normal_()
-            self.unif.uniform_()
+            check(lib.sv_noise_fill(ptr(self.eps), self.eps.numel(), ptr(self.unif), self.unif.numel(), ptr(self.noise_state),
+                                    _abi.stream()))
 
     def _sequence(self, parts=(0, 1, 2)):
         """parts: 0 = forwards, losses, backward of [P2|P4] and the decoder backward of [P1|P3] (after it the
@@ -228,7 +236,7 @@ class TrainStep:
         cp = pad16(ch)
         A, Bc = self.ctxA, self.ctxB
         self.ctxS.reset()
-        self.terms.zero_()
+        check(lib.sv_fill_zero(ptr(self.terms), self.terms.numel() * 4, st))
         net.pack_weights()
         self._noise()
         # ---- forward of [P1 | P3]
@@ -338,7 +346,6 @@ class TrainStep:
         net, A, Bc, st = self.net, self.ctxA, self.ctxB, _abi.stream()
         # ---- optimizer + BatchNorm running statistics
         check(lib.sv_sgd_step(ptr(net.params), ptr(net.grads), ptr(net.momentum), ptr(self.sgd_hyper), net.n_params, st))
-        self.kl_sum.add_(self.terms[10:11])      # device-side accumulator: the epoch average needs no per-step host sync
         if self.m2:
             net.bn_running_update([(A, 0), (A, 1)])
         else:

@@ -178,10 +178,8 @@ class Ctx:
     def reset(self):
         if self.parent is not None:
             return              # the parent's arena covers the views
-        if self.zero_used:
-            self.zero_arena[:self.zero_used].zero_()
-        else:
-            self.zero_arena.zero_()
+        n = self.zero_used if self.zero_used else self.zero_arena.numel()
+        check(lib.sv_fill_zero(ptr(self.zero_arena), n * 4, _abi.stream()))
 
 
 # ------------------------------------------------------------------------------------ the net
@@ -720,7 +718,7 @@ class Net:
             if self._igemm(ctx, k0, g_out, k0, NB, Ho, Ho, Ho, Ho, out=g_in, OHf=Hin, OWf=Hin, stats=bnb["stats"], bnb=bnb):
                 return True
         if len(phases) < s * s:
-            g_in.zero_()
+            check(lib.sv_fill_zero(ptr(g_in), g_in.numel() * g_in.element_size(), _abi.stream()))
         fused = False
         for py, px in phases:
             self._igemm(ctx, "%s.d%d%d" % (key, py, px), g_out, "%s.d%d%d" % (key, py, px), NB, Ho, Ho, Ho, Ho, out=g_in,

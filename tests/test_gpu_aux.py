@@ -348,3 +348,37 @@ def test_trainer_epoch_tail_batches_checkpoint_and_resume():
     assert tc.base_ewm == pytest.approx(1e-3)            # the reference pickles ewm AFTER its x5 at the first milestone
     r = tc.train_epoch(lu[:1], ll[:1], 3)
     assert r["steps"] == 1 and np.isfinite(r["kl_inference"])
+
+
+def test_device_noise_kernel_statistics_and_replay():
+    """sv_noise_fill (Philox4x32-10, the fused step's device noise): N(0,1) / U[0,1) moments, a fresh draw per launch (the
+    device-side offset advances, so CUDA-graph replays differ), and reproducibility from the same (seed, offset) state"""
+    from shotvae_b200 import _abi
+    from shotvae_b200._abi import lib, check, ptr
+    assert lib.sv_sizeof_noise_state() == 32
+    n, m = 4 * 128 * 128 + 3, 2 * 128 * 10 + 1                 # (not multiples of 4: tail handling)
+    st = _abi.stream()
+    state = torch.tensor([1234567, 1 << 40, 0, 0], dtype=torch.int64, device="cuda")
+    eps, u = torch.full((n,), float("nan"), device="cuda"), torch.full((m,), float("nan"), device="cuda")
+    check(lib.sv_noise_fill(ptr(eps), n, ptr(u), m, ptr(state), st))
+    e1, u1 = eps.clone(), u.clone()
+    assert torch.isfinite(e1).all() and abs(float(e1.mean())) < 0.02 and abs(float(e1.var()) - 1.0) < 0.03
+    assert abs(float((e1 ** 4).mean()) - 3.0) < 0.2                                       # kurtosis of a normal
+    assert float(u1.min()) >= 0.0 and float(u1.max()) < 1.0 and abs(float(u1.mean()) - 0.5) < 0.03
+    assert int(state[1]) == (1 << 40) + (n + 3) // 4 + (m + 3) // 4 and int(state[2]) == 0
+    # graph replay draws fresh numbers
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        check(lib.sv_noise_fill(ptr(eps), n, ptr(u), m, ptr(state), _abi.stream()))
+    g.replay(); torch.cuda.synchronize()
+    e2 = eps.clone()
+    g.replay(); torch.cuda.synchronize()
+    assert not torch.equal(e2, eps) and not torch.equal(e1, e2)
+    assert abs(float((e1 * e2).mean())) < 0.02                                            # consecutive draws are uncorrelated
+    # same state -> same numbers
+    state.copy_(torch.tensor([1234567, 1 << 40, 0, 0], dtype=torch.int64))
+    check(lib.sv_noise_fill(ptr(eps), n, ptr(u), m, ptr(state), st))
+    assert torch.equal(eps, e1) and torch.equal(u, u1)
+    buf = torch.ones(1001, device="cuda")
+    check(lib.sv_fill_zero(ptr(buf), 1000 * 4, st))
+    assert float(buf[:1000].abs().max()) == 0.0 and float(buf[1000]) == 1.0
