@@ -21,6 +21,7 @@
 // (2 issuers: 47, 4 issuers: 72 B/cycle/SM = the L2 fabric limit).  The A and B loads of consecutive k-blocks are
 // therefore dealt round-robin to six producer warps; a stage's full barrier counts two arrivals (A and B).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "igemm.h"
 
@@ -44,6 +45,7 @@ struct TcParams {
   int m_tiles, n_tiles, BN, KB;
   int rows_per_group, groups;
   int stages;
+  int pair_tiles;            // CL2: ceil(m_tiles / 2) * n_tiles tile pairs (adjacent m-tiles, same n-tile) shared by a CTA pair
   int in_stride;             // 1, or 2: the A boxes sample every second pixel (tensor-map element strides)
   int swizzle_bytes;         // 64 or 128
   int8_t dy[SV_MAX_TAPS];
@@ -100,6 +102,26 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// multicast variants (2-CTA cluster): the box lands at the same CTA-relative offset in every CTA of `mask`, and completes
+// transaction bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -135,6 +157,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
   return d;
 }
 
+// CL2: launched as clusters of two CTAs that work on adjacent m-tiles of the SAME channel tile in lockstep.  The B (weight) tile
+// of a k-block is then identical for both: each CTA fetches half of its rows from L2 and multicasts them into both CTAs' shared
+// memory, which halves the weight traffic out of L2 (the wide layers are bound by operand delivery, not by the tensor pipe).
+// Protocol changes against the single-CTA kernel: a stage may be refilled only when BOTH CTAs' MMAs have read it (the MMA
+// commit is multicast to both empty barriers, which count two arrivals); cluster barriers after the mbarrier initialisation
+// and before exit (no CTA may leave while its peer can still write into it).  MMAs, TMEM and the epilogue stay per CTA.
+template <bool CL2>
 __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full[2], tmem_empty[2];
@@ -148,12 +177,17 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = BM * p.KB * 2, b_bytes = p.BN * p.KB * 2;
   const uint32_t stage_bytes = (a_bytes + b_bytes + 1023) & ~1023u;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // tile walk: single CTA: tile = mt * n_tiles + nt over the grid; CL2: the cluster walks tile PAIRS, CTA `rank` takes m-tile
+  // 2 * pair_m + rank (a phantom tile past the end still runs -- its A boxes are out of bounds = zeros, its rows are not stored)
+  const int rank = CL2 ? (int)cluster_ctarank() : 0;
+  const int walk0 = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int walk_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = CL2 ? p.pair_tiles : p.m_tiles * p.n_tiles;
   const int KT = p.T * p.KC;
   const uint32_t tmem_cols = p.BN <= 32 ? 64 : (p.BN <= 64 ? 128 : (p.BN <= 128 ? 256 : 512));   // two accumulator stages
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], CL2 ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -165,6 +199,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();      // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
@@ -178,8 +213,9 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       int g = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      for (int tile = walk0; tile < total_tiles; tile += walk_step) {
+        const int mq = tile / p.n_tiles, nt = tile - mq * p.n_tiles;
+        const int mt = CL2 ? 2 * mq + rank : mq;
         const int img0 = (mt / p.tiles_h) * p.Nt;
         const int h0 = (mt % p.tiles_h) * p.Ht;
         for (int kb = 0; kb < KT; ++kb, ++g) {
@@ -201,8 +237,13 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
             tma_load_4d(sa, &tmA, &full_bar[stage], cb * p.KB, (int)p.dx[t], p.in_stride * h0 + (int)p.dy[t], img0);
           }
           if (do_b) {
-            mbar_expect_tx(&full_bar[stage], b_bytes);
-            tma_load_3d(sa + a_bytes, &tmB, &full_bar[stage], cb * p.KB, nt * p.BN, t);
+            mbar_expect_tx(&full_bar[stage], b_bytes);      // the whole B tile lands here: one half from each CTA of the pair when CL2
+            if (CL2) {
+              const uint32_t half = b_bytes >> 1;
+              tma_load_3d_mc(sa + a_bytes + (uint32_t)rank * half, &tmB, &full_bar[stage], cb * p.KB, nt * p.BN + rank * (p.BN >> 1), t, (uint16_t)3);
+            } else {
+              tma_load_3d(sa + a_bytes, &tmB, &full_bar[stage], cb * p.KB, nt * p.BN, t);
+            }
           }
         }
       }
@@ -217,7 +258,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = walk0; tile < total_tiles; tile += walk_step) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
@@ -235,7 +276,8 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
 #pragma unroll
             for (int k = 0; k < 2; ++k) tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);        // smem slot is free once these MMAs have read it
+          if (CL2) tc_commit_mc(&empty_bar[stage], (uint16_t)3);   // both CTAs' producers write this slot: tell both
+          else tc_commit(&empty_bar[stage]);                       // smem slot is free once these MMAs have read it
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -252,8 +294,9 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
     const int ohw = p.OH * p.OW;
     const bool bnb = p.bn_y != nullptr;
     int coef_nt = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+    for (int tile = walk0; tile < total_tiles; tile += walk_step) {
+      const int mq = tile / p.n_tiles, nt = tile - mq * p.n_tiles;
+      const int mt = CL2 ? 2 * mq + rank : mq;
       if (bnb && nt != coef_nt) {
         // coefficients of this channel tile for every pass group (a CTA's tiles mostly share nt: refilled on change only)
         asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -274,7 +317,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
       const int nb = mm / ohw, r = mm - nb * ohw;
       const int oh = r / p.OW, ow = r - oh * p.OW;
       const size_t pix = ((size_t)nb * p.OHf + oh * p.out_stride + p.out_off_y) * p.OWf + ow * p.out_stride + p.out_off_x;
-      const int g = (mt * BM) / p.rows_per_group;
+      const int g = min((mt * BM) / p.rows_per_group, p.groups - 1);      // (clamped: a CL2 phantom tile lies past the last group)
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t raw[16];
@@ -362,6 +405,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();      // the peer may still multicast into this CTA / arrive on its barriers until it is done too
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -418,7 +462,13 @@ int sm_count() {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 igemm_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams p) {
-  tc_kernel_body(tmA, tmB, p);
+  tc_kernel_body<false>(tmA, tmB, p);
+}
+
+// launched with cluster dimension 2 (launch attribute)
+__global__ void __launch_bounds__(TC_THREADS, 1)
+igemm_fprop_tc_cl2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams p) {
+  tc_kernel_body<true>(tmA, tmB, p);
 }
 
 // Up to four independent problems of identical tile shape in ONE grid (blockIdx.y selects the problem): the four
@@ -432,19 +482,28 @@ struct TcBatch {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) igemm_fprop_tc_batched_kernel(const __grid_constant__ TcBatch b) {
   const int ph = blockIdx.y;
-  tc_kernel_body(b.tmA[ph], b.tmB[ph], b.p[ph]);
+  tc_kernel_body<false>(b.tmA[ph], b.tmB[ph], b.p[ph]);
 }
 
 }  // namespace
 
-// channel tile: whole N up to 128; beyond that the largest multiple of 16 that divides N and fits one MMA (<= 256)
-// whose tile still leaves >= 4 shared-memory stages (160 for N = 160 / 320, 128 for N = 256 / 512 / 640)
-static int pick_bn(int N) {
-  if (N <= 128) return N;
-  if (N % 128 == 0) return 128;
-  for (int bn = 192; bn >= 64; bn -= 16)
-    if (N % bn == 0) return bn;
+// channel tile.  MEASURED (profiles/r02_kernel_findings.md section 6): the wide layers are bound by operand delivery into shared
+// memory, not by the tensor pipe, and the operand bytes per MAC fall with the tile width (A tile 16 KB + B tile BN/8 KB per
+// 128 x BN x 64 MACs): the widest tile (a multiple of 16 that divides N, <= 256 = one MMA, >= 4 shared-memory stages of 64-channel
+// k-blocks) wins as long as the persistent grid stays filled -- C4 25.6 -> 24.9 ms/step against the 128-column cap
+// (SHOTVAE_TC_BN=128 restores it).  Tiles wider than one MMA (320 columns as two N = 160 MMAs over one A tile, which needs
+// 32-channel k-blocks and a single accumulator stage) were MEASURED twice as slow: the kernel is bound by the NUMBER of TMA loads.
+static int next_bn_below(int N, int bn) {
+  for (int b = bn - 16; b >= 16; b -= 16)
+    if (N % b == 0) return b;
   return 0;
+}
+
+static int pick_bn(int N) {
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("SHOTVAE_TC_BN"); cap = e ? atoi(e) : 256; if (cap < 64 || cap > 256) cap = 256; }
+  if (N <= 128) return N;
+  return next_bn_below(N, (N < cap ? N : cap) + 16);
 }
 
 bool igemm_fprop_tc_supported(const IgemmParams& p) {
@@ -466,7 +525,10 @@ bool igemm_fprop_tc_supported(const IgemmParams& p) {
   return get_encode() != nullptr;
 }
 
-static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtensorMap& tmB, size_t& smem, int& grid) {
+static int max_active_clusters(size_t smem);
+
+// cl2 (in/out): in = a 2-CTA cluster launch is possible for the caller; out = this problem should use it
+static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtensorMap& tmB, size_t& smem, int& grid, bool* cl2 = nullptr) {
   EncodeTiledFn encode = get_encode();
   if (!encode) { sv_set_error("cuTensorMapEncodeTiled unavailable"); return SV_ERR_UNSUPPORTED; }
   TileGeom g;
@@ -485,7 +547,11 @@ static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtenso
   q.m_tiles = ceil_div(p.M, BM);
   // channel tile: whole N when small; otherwise split so that the persistent grid is filled
   int bn = pick_bn(p.N);
-  while (bn <= 128 && bn > 32 && bn % 32 == 0 && q.m_tiles * (p.N / bn) < sm_count() && p.N % (bn / 2) == 0) bn /= 2;
+  while (bn > 32 && q.m_tiles * (p.N / bn) < sm_count()) {
+    const int nb = next_bn_below(p.N, bn);
+    if (nb < 32) break;
+    bn = nb;
+  }
   q.BN = bn;
   q.n_tiles = p.N / bn;
   q.rows_per_group = p.rows_per_group;
@@ -502,6 +568,21 @@ static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtenso
   memcpy(q.dy, p.dy, SV_MAX_TAPS);
   memcpy(q.dx, p.dx, SV_MAX_TAPS);
 
+  smem = (size_t)stages * stage_bytes + 1024;
+  // CTA pairs with multicast weight tiles: wide channel tiles (that is where the weight traffic is), enough tile pairs to keep
+  // every resident cluster busy for at least two rounds; SHOTVAE_TC_CLUSTER=0 turns it off (A/B switch)
+  bool use_cl2 = false;
+  if (cl2 != nullptr && *cl2) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SHOTVAE_TC_CLUSTER"); on = (e && e[0] == '0') ? 0 : 1; }
+    q.pair_tiles = ceil_div(q.m_tiles, 2) * q.n_tiles;
+    const int clusters = on ? max_active_clusters(smem) : 0;
+    // MEASURED on C4 (profiles/r02_kernel_findings.md section 6): +10 % on the layers whose channel tile is the whole N (160-channel
+    // block: 843 -> 929 TFLOP/s), -4 % where N is split into several tiles (320 / 640 channels) -> only the former take it
+    use_cl2 = clusters >= 32 && q.BN >= 128 && q.n_tiles == 1 && q.pair_tiles >= 2 * clusters;
+    if (use_cl2) grid = 2 * clusters;
+    *cl2 = use_cl2;
+  }
   const CUtensorMapSwizzle sw = q.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.NB};
@@ -516,15 +597,16 @@ static int tc_setup(const IgemmParams& p, TcParams& q, CUtensorMap& tmA, CUtenso
   {
     cuuint64_t dims[3] = {(cuuint64_t)p.C, (cuuint64_t)p.N, (cuuint64_t)p.T};
     cuuint64_t strides[2] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.N * p.C * 2};
-    cuuint32_t box[3] = {(cuuint32_t)q.KB, (cuuint32_t)q.BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)q.KB, (cuuint32_t)(use_cl2 ? q.BN / 2 : q.BN), 1};     // CL2: each CTA of the pair fetches half the rows
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(p.Wt), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sv_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return SV_ERR_CUDA; }
   }
-  smem = (size_t)stages * stage_bytes + 1024;
-  const int total = q.m_tiles * q.n_tiles;
-  grid = total < sm_count() ? total : sm_count();
+  if (!use_cl2) {
+    const int total = q.m_tiles * q.n_tiles;
+    grid = total < sm_count() ? total : sm_count();
+  }
   return SV_OK;
 }
 
@@ -532,9 +614,34 @@ static void tc_configure() {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(igemm_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(igemm_fprop_tc_cl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(igemm_fprop_tc_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
+}
+
+// how many 2-CTA clusters of the CL2 kernel can be resident at once (1 CTA per SM, pairs inside one GPC): the persistent grid
+// must not exceed it, or the surplus clusters would run as a second wave
+static int max_active_clusters(size_t smem) {
+  static int cached = -1;
+  static size_t cached_smem = 0;
+  if (cached >= 0 && cached_smem == smem) return cached;
+  tc_configure();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(sm_count() & ~1);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, igemm_fprop_tc_cl2_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (n > sm_count() / 2) n = sm_count() / 2;
+  cached = n; cached_smem = smem;
+  return n;
 }
 
 int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st) {
@@ -542,9 +649,27 @@ int igemm_fprop_tc(const IgemmParams& p, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   size_t smem;
   int grid;
-  const int rc = tc_setup(p, q, tmA, tmB, smem, grid);
+  bool cl2 = true;
+  const int rc = tc_setup(p, q, tmA, tmB, smem, grid, &cl2);
   if (rc != SV_OK) return rc;
   tc_configure();
+  if (cl2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = sv_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaLaunchKernelEx(&cfg, igemm_fprop_tc_cl2_kernel, tmA, tmB, q);
+    return sv_check_launch("igemm_fprop_tc_cl2");
+  }
   sv_launch_pdl(igemm_fprop_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, q);
   return sv_check_launch("igemm_fprop_tc");
 }

@@ -164,6 +164,33 @@ def test_conv_fprop_benchmark_batch_matches_torch(sv, cin, cout, H, k, NB, G):
     assert torch.equal(out, out2)
 
 
+# wide layers on the TMA kernel at sizes that fill the machine (WRN-28-10): the widest channel tile (160 / 256 columns) and, with
+# >= 2 x 74 tile pairs, the 2-CTA cluster variant whose weight tiles are fetched half by each CTA and multicast to both
+@pytest.mark.parametrize("cin,cout,H,k,NB,G", [(320, 320, 16, 3, 80, 2), (640, 640, 8, 3, 160, 4), (160, 160, 32, 3, 20, 2), (256, 256, 8, 3, 304, 1),
+                                               (160, 320, 16, 1, 80, 1),
+                                               (640, 640, 8, 3, 150, 1), (320, 160, 16, 3, 160, 4)])     # (odd tile count: phantom tile of a CTA pair)
+def test_conv_fprop_wide_tiles_match_torch(sv, cin, cout, H, k, NB, G):
+    from shotvae_b200.plan import conv_taps
+    torch.manual_seed(cin + cout + H + NB)
+    x, w = bf(torch.randn(NB, cin, H, H)), bf(torch.randn(cout, cin, k, k) * 0.05)
+    resid = bf(torch.randn(NB, cout, H, H))
+    torch.set_num_threads(max(1, (os.cpu_count() or 8)))
+    want = F.conv2d(x, w, None, 1, k // 2) + resid
+    taps = conv_taps(k, k // 2)
+    Wt = pack(sv, w, cout, cin, taps, cout, cin, cin * k * k, k * k, 1, 2)
+    out = torch.empty(NB, H, H, cout, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(G, 2, cout, device="cuda")
+    igemm(sv, nhwc(x), Wt, taps, NB, H, H, cin, H, H, cout, out=out, res=nhwc(resid), stats=stats, group_images=NB // G, impl=2)
+    got = from_nhwc(out)
+    assert rel_rms(got, want) < 4e-3
+    gq = got.view(G, NB // G, cout, -1)
+    assert rel_rms(stats[:, 0].cpu(), gq.sum(dim=(1, 3))) < 2e-3
+    assert rel_rms(stats[:, 1].cpu(), (gq * gq).sum(dim=(1, 3))) < 1e-3
+    out2 = torch.empty_like(out)
+    igemm(sv, nhwc(x), Wt, taps, NB, H, H, cin, H, H, cout, out=out2, res=nhwc(resid), impl=2)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("cin,cout,H,k", WRN282_SHAPES)
 def test_conv_wgrad_benchmark_batch_matches_autograd(sv, cin, cout, H, k):
     from shotvae_b200.plan import conv_taps
