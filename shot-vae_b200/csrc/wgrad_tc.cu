@@ -26,7 +26,8 @@
 
 namespace {
 
-constexpr int WT_THREADS = 416;
+constexpr int WT_THREADS = 544;          // 17 warps: MMA, 4 epilogue, up to 12 TMA producers
+constexpr int MAX_A_STAGES = 3;
 constexpr int BLK = 128;                 // pixels per block = channels per n-tile
 constexpr uint32_t BOX_BYTES = 64 * BLK * 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
@@ -38,6 +39,7 @@ struct WtcParams {
   int Nt, Ht, tiles_h;       // box geometry (images, rows per block; blocks per image column)
   int cb, c_blocks, boxes;   // channels per MMA (N of the instruction), C / cb, ceil(cb / 64)
   int pairs, ppu, units_per_nt, splits;
+  int a_stages;              // activation stages in shared memory: 3 while they fit (<= 3 boxes per stage), else 2
   int in_stride;             // 1, or 2: the activation boxes sample every second pixel (tensor-map element strides)
   int8_t dy[SV_MAX_TAPS];
   int8_t dx[SV_MAX_TAPS];
@@ -113,7 +115,7 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo
 __global__ void __launch_bounds__(WT_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ WtcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t g_full[2], g_empty[2], a_full[2], a_empty[2], done_bar;
+  __shared__ uint64_t g_full[2], g_empty[2], a_full[MAX_A_STAGES], a_empty[MAX_A_STAGES], done_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -128,10 +130,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   const int pb0 = (int)((long long)slice * p.PB / p.splits), pb1 = (int)((long long)(slice + 1) * p.PB / p.splits);
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&g_full[s], 2); mbar_init(&g_empty[s], 1);
-      mbar_init(&a_full[s], (uint32_t)p.boxes); mbar_init(&a_empty[s], 1);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&g_full[s], 2); mbar_init(&g_empty[s], 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], (uint32_t)p.boxes); mbar_init(&a_empty[s], 1); }
     mbar_init(&done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -144,25 +144,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  const int prod = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : (warp >= 8 && warp <= 12 ? warp - 5 : -1)));
+  // producer 4 * stage + b owns box slot b of activation stage `stage` (and, for stage < 2 and b < 2, of the G stage)
+  const int prod = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : (warp >= 8 && warp <= 16 ? warp - 5 : -1)));
   if (prod >= 0) {
     // ===================================== TMA producers =====================================
     const int ps = prod >> 2, pbx = prod & 3;       // the stage and the box slot this producer owns
-    if (lane == 0 && (pbx < p.boxes || pbx < 2)) {
+    if (lane == 0 && ps < p.a_stages && (pbx < p.boxes || (pbx < 2 && ps < 2))) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       int gi = 0, ai = 0;       // G stages / A stages filled so far
       for (int pb = pb0; pb < pb1; ++pb, ++gi) {
         const int img0 = (pb / p.tiles_h) * p.Nt, h0 = (pb % p.tiles_h) * p.Ht;
-        if ((gi & 1) == ps && pbx < 2) {
+        if (ps < 2 && (gi & 1) == ps && pbx < 2) {
           mbar_wait(&g_empty[ps], (uint32_t)(((gi >> 1) & 1) ^ 1));
           mbar_expect_tx(&g_full[ps], BOX_BYTES);
           tma_load_4d(g_base + ps * g_stage + pbx * BOX_BYTES, &tmG, &g_full[ps], nt * BLK + 64 * pbx, 0, h0, img0);
         }
         for (int pr = 0; pr < npair; ++pr, ++ai) {
-          if ((ai & 1) != ps || pbx >= p.boxes) continue;
+          if (ai % p.a_stages != ps || pbx >= p.boxes) continue;
           const int pair = pair0 + pr, t = pair / p.c_blocks, cblk = pair - t * p.c_blocks;
-          mbar_wait(&a_empty[ps], (uint32_t)(((ai >> 1) & 1) ^ 1));
+          mbar_wait(&a_empty[ps], (uint32_t)(((ai / p.a_stages) & 1) ^ 1));
           mbar_expect_tx(&a_full[ps], BOX_BYTES);
           tma_load_4d(a_base + ps * a_stage + pbx * BOX_BYTES, &tmA, &a_full[ps], cblk * p.cb + 64 * pbx, (int)p.dx[t], p.in_stride * h0 + (int)p.dy[t], img0);
         }
@@ -179,8 +180,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
       tc_fence_after();
       const uint64_t gdesc = make_desc_mn128(g_base + gs * g_stage, BOX_BYTES, 1024);
       for (int pr = 0; pr < npair; ++pr, ++ai) {
-        const int as = ai & 1;
-        mbar_wait(&a_full[as], (uint32_t)((ai >> 1) & 1));
+        const int as = ai % p.a_stages;
+        mbar_wait(&a_full[as], (uint32_t)((ai / p.a_stages) & 1));
         tc_fence_after();
         const uint64_t adesc = make_desc_mn128(a_base + as * a_stage, BOX_BYTES, 1024);
         const uint32_t d_tmem = tmem_base + (uint32_t)(pr * p.cb);
@@ -284,6 +285,7 @@ bool geometry(const WgradParams& p, WtcParams& q) {
   if (q.cb == 0) return false;
   q.c_blocks = p.C / q.cb;
   q.boxes = ceil_div(q.cb, 64);
+  q.a_stages = q.boxes <= 3 ? MAX_A_STAGES : 2;      // 2 G stages (64 KB) + 3 x 48 KB or 2 x 64 KB of activation stages
   q.pairs = p.T * q.c_blocks;
   q.ppu = 512 / q.cb;
   q.units_per_nt = ceil_div(q.pairs, q.ppu);
@@ -344,10 +346,10 @@ int wgrad_tc(const WgradParams& p, cudaStream_t st) {
   }
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     configured = true;
   }
-  const size_t smem = (size_t)(2 * 2 + 2 * q.boxes) * BOX_BYTES + 1024;
+  const size_t smem = (size_t)(2 * 2 + q.a_stages * q.boxes) * BOX_BYTES + 1024;
   const int grid = ceil_div(p.N, BLK) * q.units_per_nt * q.splits;
   wgrad_tc_kernel<<<grid, WT_THREADS, smem, st>>>(tmG, tmA, q);
   return sv_check_launch("wgrad_tc");
