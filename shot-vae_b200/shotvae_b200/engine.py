@@ -61,6 +61,7 @@ class TrainStep:
         # SHOTVAE_DDP_GRAPH=single captures the all-reduces into ONE graph instead (works: NCCL supports stream capture) --
         # MEASURED at 2 GPUs: 5.005 vs 5.021 ms/step, i.e. the host-side gaps are not what the 2 % data-parallel overhead is made
         # of, and destroy_process_group() hung for minutes with the captured communicator still referenced -> opt-in only
+        self.fwd_overlap = os.environ.get("SHOTVAE_FWD_OVERLAP", "1") != "0"
         self.ddp_single_graph = os.environ.get("SHOTVAE_DDP_GRAPH", "segments") == "single"
         # weight gradients overlap the dgrad / BatchNorm-backward chain on a second stream (SHOTVAE_SIDE=0 turns it off)
         if net.side is None and os.environ.get("SHOTVAE_SIDE", "1") != "0":
@@ -239,6 +240,24 @@ class TrainStep:
         check(lib.sv_fill_zero(ptr(self.terms), self.terms.numel() * 4, st))
         net.pack_weights()
         self._noise()
+        # Without --om the inputs of [P2 | P4] are mixtures of the INPUT images under host-drawn pairings: their encoder forward
+        # depends on nothing [P1 | P3] computes (only the loss targets do), so it runs on a second stream beside the first one.
+        # Every conv kernel is a persistent 148-CTA grid of 15-25 us with ~45 % of that in prologue / first-tile latency / tail
+        # (profiles/r02_kernel_findings.md): two independent chains fill each other's gaps.  SHOTVAE_FWD_OVERLAP=0: one after the other.
+        conc = (not self.m2) and (not self.h["om"]) and (not net.f32) and net.side is not None and self.side2 is not None and self.fwd_overlap
+        if conc:
+            ev0 = torch.cuda.Event()
+            ev0.record(torch.cuda.current_stream())
+            self.side2.wait_event(ev0)
+            with torch.cuda.stream(self.side2):
+                s2 = _abi.stream()
+                xB = Bc.t("x_img", (2 * B, 32, 32, cp))
+                check(lib.sv_mixup_lerp(ptr(self.img_l), None, None, None, ptr(self.idx_l), ptr(self.lam), B, ch, 32 * 32, D, nd, None,
+                                        ptr(xB[:B]), cp, None, None, None, s2))
+                check(lib.sv_mixup_lerp(ptr(self.img_u), None, None, None, ptr(self.idx_u), ptr(self.lam[2:]), B, ch, 32 * 32, D, nd, None,
+                                        ptr(xB[B:]), cp, None, None, None, s2))
+                featB = net.encoder_fwd(Bc, xB)
+                mu2, ls2, la2 = net.heads_fwd(Bc, featB)
         # ---- forward of [P1 | P3]
         xA = A.t("x_img", (2 * B, 32, 32, cp))
         check(net.fn("sv_pack_image")(ptr(self.img_l), ptr(xA[:B]), B, ch, 32 * 32, cp, st))
@@ -273,7 +292,14 @@ class TrainStep:
             # backward of [P1 | P3]: decoder first (its gradients are final afterwards)
             self._g_lat = net.decoder_bwd(A, g_rec)
             self._g = (g_mu, g_ls, g_la)
-        if not self.m2:
+        if conc:
+            # the mixing targets of the posterior terms need [P1 | P3]'s latents; then join the second forward
+            check(lib.sv_mixup_lerp(None, ptr(mu[:B]), ptr(ls[:B]), ptr(la[:B]), ptr(self.idx_l), ptr(self.lam), B, ch, 32 * 32, D, nd,
+                                    None, None, 0, ptr(self.s_mu), ptr(self.s_sig), ptr(self.s_alpha), st))
+            check(lib.sv_mixup_lerp(None, ptr(mu[B:]), ptr(ls[B:]), ptr(la[B:]), ptr(self.idx_u), ptr(self.lam[2:]), B, ch, 32 * 32, D, nd,
+                                    None, None, 0, ptr(self.m_mu), ptr(self.m_sig), ptr(self.m_alpha), st))
+            main.wait_stream(self.side2)
+        elif not self.m2:
             # ---- label smoothing (P1 -> P2 inputs) and optimal-interpolation mixup (P3 -> P4 inputs)
             xB = Bc.t("x_img", (2 * B, 32, 32, cp))
             # (FP32 mode: the mixed images are written as fp32 NCHW and then laid out NHWC like any input batch)
@@ -292,6 +318,7 @@ class TrainStep:
             # ---- forward of [P2 | P4]
             featB = net.encoder_fwd(Bc, xB)
             mu2, ls2, la2 = net.heads_fwd(Bc, featB)
+        if not self.m2:
             # (the decoder forwards of P2/P4 -- kept only for their BatchNorm running statistics -- run beside the
             # encoder backward in part 1: nothing in the step waits for them before the running-statistics update)
             g_mu2, g_ls2, g_la2 = Bc.t("g.mu", (2 * B, D), torch.float32), Bc.t("g.ls", (2 * B, D), torch.float32), \
