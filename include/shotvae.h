@@ -115,6 +115,19 @@ int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits, int32_t N
                     int32_t n_real, int32_t c_real, int64_t sn, int64_t sc, int64_t st,
                     const int8_t* tap_index /* host, T entries */, void* stream);
 
+/* The same reduction for several weight tensors in ONE launch (launch latency, not bytes, is what 30-odd small reductions
+ * per step cost): descs is a HOST array, every record has the meaning of the sv_wgrad_reduce arguments.  The partial buffers
+ * must all be live until the launch has run (one workspace per weight tensor, not a shared one). */
+typedef struct {
+  const float* partial;
+  float* grad;
+  int64_t sn, sc, st;
+  int32_t splits, N, C, T, n_real, c_real;
+  int8_t tap_index[SV_MAX_TAPS];
+} sv_wgrad_reduce_desc;
+int sv_wgrad_reduce_batched(const sv_wgrad_reduce_desc* descs /* host */, int32_t n, void* stream);
+int sv_sizeof_wgrad_reduce_desc(void);
+
 /* dst(t, n, c) (bf16) = src[n*sn + c*sc + tap_index[t]*st] for n < n_real, c < c_real else 0;
  * layout 0: dst[t][n][c]; layout 1: dst[t][c/8][n][c%8] (8-channel planes, for the halo-tile kernel);
  * layout 2: dst is FLOAT [t][n][c] (FP32 mode) */
@@ -207,6 +220,26 @@ int sv_linear_bwd_input(const float* g_f32, const void* g_bf16, int32_t ldg, con
 /* dW(n,k) += sum_b g[b][n] * x[b][k]; dbias[n] += sum_b g[b][n] */
 int sv_linear_bwd_weight(const float* g_f32, const void* g_bf16, int32_t ldg, const float* x, int32_t ldx, float* dW,
                          int32_t ldw, int32_t w_kn, float* dbias, int32_t B, int32_t N, int32_t K, void* stream);
+/* The inference heads of the VAE (vae.py:113-129: continuous mean, continuous log sigma, discrete logits) share their input:
+ * one launch for all of them in each direction.  W[i] is [N[i]][K] row-major (nn.Linear), out[i] / g[i] are [B][N[i]] fp32.
+ *   sv_heads_fwd:        out[i][b][n] = sum_k x[b][k] W[i][n][k] + bias[i][n]        (same arithmetic as sv_linear_fwd)
+ *   sv_heads_bwd_input:  gx[b][k]     = sum_i sum_n g[i][b][n] W[i][n][k]
+ *   sv_heads_bwd_weight: dW[i][n][k] += sum_b g[i][b][n] x[b][k];  dbias[i][n] += sum_b g[i][b][n]   (dbias[i] may be NULL) */
+#define SV_MAX_HEADS 4
+typedef struct {
+  const float* W[SV_MAX_HEADS];
+  const float* bias[SV_MAX_HEADS];
+  float* out[SV_MAX_HEADS];
+  const float* g[SV_MAX_HEADS];
+  float* dW[SV_MAX_HEADS];
+  float* dbias[SV_MAX_HEADS];
+  int32_t N[SV_MAX_HEADS];
+  int32_t n;
+} sv_heads;
+int sv_sizeof_heads(void);
+int sv_heads_fwd(const float* x, int32_t ldx, const sv_heads* heads, int32_t B, int32_t K, void* stream);
+int sv_heads_bwd_input(const sv_heads* heads, float* gx, int32_t ldgx, int32_t B, int32_t K, void* stream);
+int sv_heads_bwd_weight(const sv_heads* heads, const float* x, int32_t ldx, int32_t B, int32_t K, void* stream);
 int sv_log_softmax_fwd(const float* logits, float* out, int32_t B, int32_t N, void* stream);
 /* g_logits = g_out - exp(out) * sum_n g_out */
 int sv_log_softmax_bwd(const float* g_out, const float* out, float* g_logits, int32_t B, int32_t N, void* stream);

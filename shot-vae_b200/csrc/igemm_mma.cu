@@ -410,6 +410,47 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// Several weight tensors in ONE launch (sv_wgrad_reduce_batched): the descriptors travel as kernel parameters, block ranges
+// [first[i], first[i+1]) belong to descriptor i; inside a range the blocks are (x = element slice, y = slice of 16 partial sums)
+// exactly like the grid of wgrad_reduce_kernel.
+struct ReduceDesc {          // == sv_wgrad_reduce_desc (include/shotvae.h)
+  const float* partial;
+  float* grad;
+  long long sn, sc, st;
+  int splits, N, C, T, n_real, c_real;
+  int8_t tap[SV_MAX_TAPS];
+};
+static_assert(sizeof(ReduceDesc) == sizeof(sv_wgrad_reduce_desc), "sv_wgrad_reduce_desc layout");
+constexpr int RB_MAX = 40;   // 40 x 80 B + block table = 3.4 KB of the 4 KB parameter space
+struct ReduceBatch {
+  ReduceDesc d[RB_MAX];
+  int first[RB_MAX + 1];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const __grid_constant__ ReduceBatch b) {
+  int i = 0;
+  while (i + 1 < b.n && (int)blockIdx.x >= b.first[i + 1]) ++i;
+  const ReduceDesc& d = b.d[i];
+  const int lb = blockIdx.x - b.first[i], nblk = b.first[i + 1] - b.first[i];
+  const int ysl = (d.splits + 15) / 16, bxn = nblk / ysl;
+  const int bx = lb % bxn, by = lb / bxn;
+  const long long total = (long long)d.n_real * d.T * d.c_real;
+  const long long TC = (long long)d.T * d.C;
+  const int k0 = by * 16, k1 = min(k0 + 16, d.splits);
+  for (long long e = bx * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)bxn * blockDim.x) {
+    const int c = (int)(e % d.c_real);
+    const long long r = e / d.c_real;
+    const int t = (int)(r % d.T);
+    const int n = (int)(r / d.T);
+    const float* src = d.partial + (long long)n * TC + (long long)t * d.C + c;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) s[k & 3] += src[(long long)k * d.N * TC];
+    atomicAdd(&d.grad[n * d.sn + c * d.sc + d.tap[t] * d.st], (s[0] + s[1]) + (s[2] + s[3]));
+  }
+}
+
 __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int C, int T, int n_real,
                                    int c_real, long long sn, long long sc, long long st, TapIdx ti, int layout) {
   const long long total = (long long)T * N * C;
@@ -526,6 +567,31 @@ extern "C" int sv_wgrad_reduce(const float* partial, float* grad, int32_t splits
   sv_launch_pdl(wgrad_reduce_kernel, dim3(blocks, (splits + 15) / 16), dim3(256), 0, (cudaStream_t)stream, partial, grad, splits, N, C, T, n_real, c_real,
                                                                                           sn, sc, st, ti);
   return sv_check_launch("wgrad_reduce");
+}
+
+extern "C" int sv_sizeof_wgrad_reduce_desc() { return (int)sizeof(sv_wgrad_reduce_desc); }
+
+extern "C" int sv_wgrad_reduce_batched(const sv_wgrad_reduce_desc* descs, int32_t n, void* stream) {
+  SV_REQUIRE(descs != nullptr && n >= 0, "sv_wgrad_reduce_batched: bad arguments");
+  for (int i0 = 0; i0 < n; i0 += RB_MAX) {
+    ReduceBatch b;
+    b.n = n - i0 < RB_MAX ? n - i0 : RB_MAX;
+    int blocks = 0;
+    for (int i = 0; i < b.n; ++i) {
+      memcpy(&b.d[i], &descs[i0 + i], sizeof(ReduceDesc));
+      const ReduceDesc& d = b.d[i];
+      SV_REQUIRE(d.partial && d.grad && d.T >= 1 && d.T <= SV_MAX_TAPS && d.splits >= 1, "sv_wgrad_reduce_batched: bad descriptor");
+      const long long total = (long long)d.n_real * d.T * d.c_real;
+      const int bx = (int)((total + 255) / 256 > 148 * 4 ? 148 * 4 : (total + 255) / 256);
+      b.first[i] = blocks;
+      blocks += (bx > 0 ? bx : 1) * ((d.splits + 15) / 16);
+    }
+    b.first[b.n] = blocks;
+    wgrad_reduce_batched_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b);
+    const int rc = sv_check_launch("wgrad_reduce_batched");
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 extern "C" int sv_pack_weight(const float* src, void* dst, int32_t N, int32_t C, int32_t T, int32_t n_real,

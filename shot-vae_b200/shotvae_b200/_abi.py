@@ -37,6 +37,17 @@ class WgradArgs(C.Structure):
                 ("in_stride", i32), ("splits", i32), ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS), ("impl", i32)]
 
 
+class ReduceDesc(C.Structure):
+    _fields_ = [("partial", vp), ("grad", vp), ("sn", i64), ("sc", i64), ("st", i64),
+                ("splits", i32), ("N", i32), ("C", i32), ("T", i32), ("n_real", i32), ("c_real", i32),
+                ("tap_index", C.c_int8 * MAX_TAPS)]
+
+
+class Heads(C.Structure):
+    _fields_ = [("W", vp * 4), ("bias", vp * 4), ("out", vp * 4), ("g", vp * 4), ("dW", vp * 4), ("dbias", vp * 4),
+                ("N", i32 * 4), ("n", i32)]
+
+
 class PackDesc(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("sn", i64), ("sc", i64), ("st", i64),
                 ("N", i32), ("C", i32), ("T", i32), ("n_real", i32), ("c_real", i32), ("layout", i32),
@@ -67,6 +78,8 @@ _PROTOS = {
     "sv_igemm_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "sv_igemm_wgrad_splits": (C.c_int, [C.POINTER(WgradArgs)]),
     "sv_wgrad_reduce": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i8p, vp]),
+    "sv_wgrad_reduce_batched": (C.c_int, [C.POINTER(ReduceDesc), i32, vp]),
+    "sv_sizeof_wgrad_reduce_desc": (C.c_int, []),
     "sv_pack_weight": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i8p, i32, vp]),
     "sv_pack_weights_batched": (C.c_int, [vp, i32, i32, vp]),
     "sv_sizeof_pack_desc": (C.c_int, []),
@@ -93,6 +106,10 @@ _PROTOS = {
     "sv_linear_fwd": (C.c_int, [vp, i32, vp, i32, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp]),
     "sv_linear_bwd_input": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
     "sv_linear_bwd_weight": (C.c_int, [vp, vp, i32, vp, i32, vp, i32, i32, vp, i32, i32, i32, vp]),
+    "sv_sizeof_heads": (C.c_int, []),
+    "sv_heads_fwd": (C.c_int, [vp, i32, C.POINTER(Heads), i32, i32, vp]),
+    "sv_heads_bwd_input": (C.c_int, [C.POINTER(Heads), vp, i32, i32, i32, vp]),
+    "sv_heads_bwd_weight": (C.c_int, [C.POINTER(Heads), vp, i32, i32, i32, vp]),
     "sv_log_softmax_fwd": (C.c_int, [vp, vp, i32, i32, vp]),
     "sv_log_softmax_bwd": (C.c_int, [vp, vp, vp, i32, i32, vp]),
     "sv_sample_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, i32, i32, vp, i32, vp]),
@@ -121,7 +138,7 @@ for _name, (_res, _args) in _PROTOS.items():
 
 if lib.sv_abi_version() != 1:
     raise ImportError("libshotvae ABI version %d, binding expects 1" % lib.sv_abi_version())
-for _fn, _st in (("sv_sizeof_run_desc", RunDesc), ("sv_sizeof_pack_desc", PackDesc), ("sv_sizeof_igemm_args", IgemmArgs), ("sv_sizeof_wgrad_args", WgradArgs), ("sv_sizeof_bn_bwd_term", BnBwdTerm)):
+for _fn, _st in (("sv_sizeof_heads", Heads), ("sv_sizeof_wgrad_reduce_desc", ReduceDesc), ("sv_sizeof_run_desc", RunDesc), ("sv_sizeof_pack_desc", PackDesc), ("sv_sizeof_igemm_args", IgemmArgs), ("sv_sizeof_wgrad_args", WgradArgs), ("sv_sizeof_bn_bwd_term", BnBwdTerm)):
     if getattr(lib, _fn)() != C.sizeof(_st):
         raise ImportError("ctypes mirror of %s is %d bytes, library says %d" % (_st.__name__, C.sizeof(_st), getattr(lib, _fn)()))
 

@@ -26,7 +26,9 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 # SHOTVAE_FUSE_BNBWD=0: BatchNorm-backward statistics by the separate sv_bn_bwd_reduce pass everywhere (A/B switch)
 FUSE_BN_BWD = os.environ.get("SHOTVAE_FUSE_BNBWD", "1") != "0"
-WG_WORKSPACE_FLOATS = 24 * 1024 * 1024
+WG_WORKSPACE_FLOATS = 24 * 1024 * 1024          # cap of one weight tensor's partial-sum workspace
+# queued reductions are issued once their partial sums exceed this (about half of the 126 MB L2: the reduction should still hit)
+WG_FLUSH_BYTES = int(os.environ.get("SHOTVAE_WG_FLUSH_MB", "64")) * (1 << 20)
 
 
 def pad16(c):
@@ -221,7 +223,7 @@ class Net:
         self.nbt = torch.zeros(max(len(self.nbt_names), 1), dtype=torch.int64, device=self.device)
         for k, v in named_buffers.items():
             self.b(k).copy_(v.detach().to(self.device))
-        self.wg_ws = torch.empty(WG_WORKSPACE_FLOATS, dtype=torch.float32, device=self.device)
+        self._wg_pending, self._wg_pending_bytes = [], 0     # queued weight-gradient reductions (_wgrad / _wgrad_flush)
         self.param_epoch = 0      # advanced by whoever rewrites the FP32 masters behind torch's back (TrainStep's fused SGD)
         self.dry = False          # dry mode: build buffers / records only, launch nothing (Ctx views -> parent tape)
         self.eval_bn = False      # True: BatchNorm normalises with the running statistics (model.eval(), reference valid()/test())
@@ -402,6 +404,9 @@ class Net:
         del batch[:]
 
     def _wgrad(self, ctx, key, A, Gr, taps, NB, H, W, Cc, OH, OW, N, in_stride, wname, n_real, c_real, sn, sc, st, exact=False):
+        """weight-gradient GEMM into this tensor's OWN partial-sum workspace; the sum over the partial slices into the gradient
+        arena is queued and issued by _wgrad_flush() for several tensors in one launch (a shared workspace forced one small
+        reduction launch behind every weight gradient: 33 launches, 0.5 ms per C2 step, ~80 % of it launch latency)."""
         ent = ctx.args.get(key)
         if ent is None:
             T = len(taps)
@@ -411,39 +416,67 @@ class Net:
             if self.f32:                     # 64 x 64 output tiles of the FP32 kernel
                 tiles = ((T * Cc + 63) // 64) * ((N + 63) // 64)
             splits = max(1, min((296 + tiles - 1) // tiles, max(1, M // 256)))
-            while splits > 1 and splits * N * T * Cc > self.wg_ws.numel():
+            while splits > 1 and splits * N * T * Cc > WG_WORKSPACE_FLOATS:
                 splits -= 1
-            assert splits * N * T * Cc <= self.wg_ws.numel(), "wgrad workspace too small for %s" % key
+            assert splits * N * T * Cc <= WG_WORKSPACE_FLOATS, "wgrad workspace too small for %s" % key
             a = WgradArgs()
-            a.partial = ptr(self.wg_ws)
             a.NB, a.H, a.W, a.C, a.OH, a.OW, a.N, a.T = NB, H, W, Cc, OH, OW, N, T
             a.in_stride, a.splits = in_stride, splits
             a.dy, a.dx = taps_array([t[1] for t in taps]), taps_array([t[2] for t in taps])
             a.impl = 4 if self.f32 else (1 if self.impl == 1 else 0)
             a.A, a.Gr = ptr(A), ptr(Gr)
+            a.partial = ptr(A)               # (any non-null pointer: the workspace is sized from the answer)
             tc_splits = 0 if self.f32 else lib.sv_igemm_wgrad_splits(byref(a))     # > 0: the tcgen05 kernel runs it, one slice per CTA
             if tc_splits > 0:
                 splits = a.splits = tc_splits
-                assert splits * N * T * Cc <= self.wg_ws.numel(), "wgrad workspace too small for %s" % key
-            ent = (a, taps_array([t[0] for t in taps]), splits, T)
+                assert splits * N * T * Cc <= WG_WORKSPACE_FLOATS, "wgrad workspace too small for %s" % key
+            ws = torch.empty(splits * N * T * Cc, dtype=torch.float32, device=self.device)
+            a.partial = ptr(ws)
+            d = _abi.ReduceDesc()
+            d.partial, d.grad = ptr(ws), ptr(self.g(wname))
+            d.sn, d.sc, d.st = sn, sc, st
+            d.splits, d.N, d.C, d.T, d.n_real, d.c_real = splits, N, Cc, T, n_real, c_real
+            for i, t in enumerate(taps):
+                d.tap_index[i] = t[0]
+            ent = (a, d, ws, splits, T)
             ctx.args[key] = ent
-        a, tidx, splits, T = ent
+        a, d, ws, splits, T = ent
         a.A, a.Gr = ptr(A), ptr(Gr)
         s = _abi.stream()
+        nbytes_red = splits * N * T * Cc * 4 + n_real * c_real * T * 8
         if self.timing is not None:
             flops = 2.0 * n_real * c_real * _valid_pairs(taps, NB, OH, OW, H, W, in_stride, exact)
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
             e0.record()
             check(lib.sv_igemm_wgrad(C.byref(a), s))
             e1.record()
-            check(lib.sv_wgrad_reduce(ptr(self.wg_ws), ptr(self.g(wname)), splits, N, Cc, T, n_real, c_real, sn, sc, st, tidx, s))
-            e2.record()
             nbytes = A.numel() * 2 // (in_stride * in_stride) + Gr.numel() * 2 + splits * N * T * Cc * 4
             self.timing.append(("igemm_wgrad", key, flops, e0, e1, nbytes))
-            self.timing.append(("wgrad_reduce", key, 0.0, e1, e2, splits * N * T * Cc * 4 + n_real * c_real * T * 8))
+        else:
+            check(lib.sv_igemm_wgrad(C.byref(a), s))
+        self._wg_pending.append((key, d, nbytes_red))
+        self._wg_pending_bytes += nbytes_red
+        if self._wg_pending_bytes > WG_FLUSH_BYTES:
+            self._wgrad_flush()
+
+    def _wgrad_flush(self):
+        """sum the queued partial-sum workspaces into the gradient arena: one launch (current stream = the stream the queued
+        weight gradients were issued on)"""
+        pend = self._wg_pending
+        if not pend:
             return
-        check(lib.sv_igemm_wgrad(C.byref(a), s))
-        check(lib.sv_wgrad_reduce(ptr(self.wg_ws), ptr(self.g(wname)), splits, N, Cc, T, n_real, c_real, sn, sc, st, tidx, s))
+        arr = (_abi.ReduceDesc * len(pend))(*[d for _, d, _ in pend])
+        s = _abi.stream()
+        if self.timing is not None:
+            e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+            e0.record()
+            check(lib.sv_wgrad_reduce_batched(arr, len(pend), s))
+            e1.record()
+            self.timing.append(("wgrad_reduce", "+".join(k for k, _, _ in pend), 0.0, e0, e1, sum(b for _, _, b in pend)))
+        else:
+            check(lib.sv_wgrad_reduce_batched(arr, len(pend), s))
+        del pend[:]
+        self._wg_pending_bytes = 0
 
     def _bn_fwd(self, ctx, bn_name, key, stats, Cc, count):
         """finalize batch statistics -> (scale, shift, mean, var), all [G][C]"""
@@ -696,7 +729,11 @@ class Net:
             self._bn_bwd(ctx, k + ".bn1", terms, rec["h_in"], addend, g_prev, rows_in, Hin * Hin)
             g_h = g_prev
         if side is not None:
+            with torch.cuda.stream(side):
+                self._wgrad_flush()          # the segment's gradients are complete when the side stream is joined
             main.wait_stream(side)
+        else:
+            self._wgrad_flush()
         ctx._bwd_state = (g_h, flip)
         if not last:
             return
@@ -705,6 +742,7 @@ class Net:
         cin_p = pad16(self.in_ch)
         self._wgrad(ctx, "conv0.w", ctx.x_img, g_h, conv_taps(3, 1), NB, 32, 32, cin_p, 32, 32, f0, 1,
                     "feature_extractor.encoder.pre_process.conv0.weight", f0, self.in_ch, self.in_ch * 9, 9, 1)
+        self._wgrad_flush()
         check(self.fn("sv_colsum_bf16")(ptr(g_h), ptr(self.g("feature_extractor.encoder.pre_process.conv0.bias")), NB * 32 * 32, f0, f0,
                                         _abi.stream()))
 
@@ -728,19 +766,30 @@ class Net:
     # ---- heads + sample ------------------------------------------------------------------------
     HEADS = (("continuous_inference.mean", "mu"), ("continuous_inference.log_sigma", "ls"), ("disc_latent_inference", "logits"))
 
+    def _heads_desc(self, outs=None, grads=None):
+        """sv_heads record of the three inference heads (one launch for all of them in each direction)"""
+        h = _abi.Heads()
+        h.n = len(self.HEADS)
+        for i, (hname, short) in enumerate(self.HEADS):
+            h.N[i] = self.nd if short == "logits" else self.ldc
+            h.W[i], h.bias[i] = ptr(self.p(hname + ".fc.weight")), ptr(self.p(hname + ".fc.bias"))
+            h.dW[i], h.dbias[i] = ptr(self.g(hname + ".fc.weight")), ptr(self.g(hname + ".fc.bias"))
+            if outs is not None:
+                h.out[i] = ptr(outs[i])
+            if grads is not None:
+                h.g[i] = ptr(grads[i])
+        return h
+
     def heads_fwd(self, ctx, feat):
         NB, Cf = ctx.NB, self.topo["feat"]
         s = _abi.stream()
         outs = {}
         for hname, short in self.HEADS:
-            n = self.nd if short == "logits" else self.ldc
-            o = ctx.t(short, (NB, n), torch.float32)
-            if not self.dry:
-                check(lib.sv_linear_fwd(ptr(feat), Cf, ptr(self.p(hname + ".fc.weight")), Cf, 0, ptr(self.p(hname + ".fc.bias")),
-                                        ptr(o), None, n, None, 0, NB, n, Cf, s))
-            outs[short] = o
+            outs[short] = ctx.t(short, (NB, self.nd if short == "logits" else self.ldc), torch.float32)
         la = ctx.t("la", (NB, self.nd), torch.float32)
         if not self.dry:
+            h = self._heads_desc(outs=[outs[short] for _, short in self.HEADS])
+            check(lib.sv_heads_fwd(ptr(feat), Cf, byref(h), NB, Cf, s))
             check(lib.sv_log_softmax_fwd(ptr(outs["logits"]), ptr(la), NB, self.nd, s))
         ctx.feat = feat
         return outs["mu"], outs["ls"], la
@@ -752,12 +801,10 @@ class Net:
         g_logits = ctx.t("g.logits", (NB, self.nd), torch.float32)
         check(lib.sv_log_softmax_bwd(ptr(g_la), ptr(ctx.bufs["la"]), ptr(g_logits), NB, self.nd, s))
         g_feat = ctx.t("g.feat", (NB, Cf), torch.float32)
-        heads = [(hname, self.nd if short == "logits" else self.ldc, g) for (hname, short), g in zip(self.HEADS, (g_mu, g_ls, g_logits))]
+        h = self._heads_desc(grads=[g_mu, g_ls, g_logits])
 
         def weight_grads():
-            for hname, n, g in heads:
-                check(lib.sv_linear_bwd_weight(ptr(g), None, n, ptr(ctx.feat), Cf, ptr(self.g(hname + ".fc.weight")), Cf, 0,
-                                               ptr(self.g(hname + ".fc.bias")), NB, n, Cf, _abi.stream()))
+            check(lib.sv_heads_bwd_weight(byref(h), ptr(ctx.feat), Cf, NB, Cf, _abi.stream()))
 
         # the head weight gradients are not needed by the backward chain: side stream (joined at the end of encoder_bwd,
         # which always follows)
@@ -770,9 +817,7 @@ class Net:
                 weight_grads()
         else:
             weight_grads()
-        for i, (hname, n, g) in enumerate(heads):
-            check(lib.sv_linear_bwd_input(ptr(g), None, n, ptr(self.p(hname + ".fc.weight")), Cf, 0, ptr(g_feat), Cf,
-                                          0 if i == 0 else 1, NB, n, Cf, s))
+        check(lib.sv_heads_bwd_input(byref(h), ptr(g_feat), Cf, NB, Cf, s))
         return g_feat
 
     def sample_fwd(self, ctx, group, mode, eps, unif=None, label=None, label_mix=None, lam_dev=None):
@@ -849,6 +894,7 @@ class Net:
             g_y = ctx.t("g.d%d.y" % li, (NB, hin, hin, cin))
             self._bn_bwd(ctx, "d%d.bn" % li, [dict(rec=d["bn"], g_a=g_a, slope=0.0)], d["y"], None, g_y, B * hin * hin, hin * hin)
             g, cout, cout_p = g_y, cin, cin
+        self._wgrad_flush()
         c0 = DEC_CHANNELS[0]
         w0 = "feature_reconstructor.decoder.0.weight"
         g32, g16 = (ptr(g), None) if self.f32 else (None, ptr(g))

@@ -637,6 +637,100 @@ def test_linear_kernels_match_torch(sv):
         assert rel_rms(dW, W.grad) < 1e-5 and rel_rms(db, bias.grad) < 1e-5
 
 
+def test_linear_split_reductions_match_torch(sv):
+    """shapes that take the split paths: the decoder stem's input gradient (reduction over 1024 outputs split over gridDim.z,
+    bf16 and fp32 gradients, with and without accumulation) and batch-sliced weight gradients (B = 512)"""
+    from shotvae_b200._abi import lib, check, ptr
+    torch.manual_seed(31)
+    B, N, K = 256, 1024, 138
+    W = torch.randn(K, N)                      # ConvTranspose2d k=1 stem: [latent][c0] = W(n,k) with w_kn = 1
+    g = torch.randn(B, N)
+    st = sv.stream()
+    Wd = W.cuda()
+    for dt in (torch.float32, torch.bfloat16):
+        gd = g.to(dt).cuda()
+        want = gd.float().cpu() @ W.t()
+        gx = torch.full((B, K), 7.0, device="cuda")          # stale contents must be overwritten
+        a32, a16 = (ptr(gd), None) if dt == torch.float32 else (None, ptr(gd))
+        check(lib.sv_linear_bwd_input(a32, a16, N, ptr(Wd), N, 1, ptr(gx), K, 0, B, N, K, st))
+        assert rel_rms(gx, want) < 1e-5
+        check(lib.sv_linear_bwd_input(a32, a16, N, ptr(Wd), N, 1, ptr(gx), K, 1, B, N, K, st))
+        assert rel_rms(gx, 2 * want) < 1e-5
+    for Bw, Nw, Kw, kn in ((512, 128, 128, 0), (512, 10, 128, 0), (256, 1024, 138, 1), (200, 100, 128, 0)):
+        x, gw = torch.randn(Bw, Kw), torch.randn(Bw, Nw)
+        want_w = (x.t() @ gw) if kn else (gw.t() @ x)
+        dW, db = torch.ones_like(want_w).cuda(), torch.ones(Nw, device="cuda")     # += semantics
+        gwd, xd = gw.cuda(), x.cuda()
+        check(lib.sv_linear_bwd_weight(ptr(gwd), None, Nw, ptr(xd), Kw, ptr(dW), Nw if kn else Kw, kn, ptr(db), Bw, Nw, Kw, st))
+        assert rel_rms(dW, want_w + 1) < 1e-5 and rel_rms(db, gw.sum(0) + 1) < 1e-5
+
+
+@pytest.mark.parametrize("B,nd", [(512, 10), (200, 100), (24, 10)])
+def test_heads_launches_match_torch(sv, B, nd):
+    """sv_heads_fwd / sv_heads_bwd_input / sv_heads_bwd_weight (the three inference heads of vae.py:113-129 in one launch each)
+    against torch FP32; the forward is the arithmetic of sv_linear_fwd, so the two must agree bit for bit"""
+    from shotvae_b200._abi import lib, check, ptr, Heads
+    torch.manual_seed(37)
+    K, Ns = 128, (128, 128, nd)
+    x = torch.randn(B, K)
+    Ws = [torch.randn(n, K) * 0.1 for n in Ns]
+    bs = [torch.randn(n) for n in Ns]
+    gs = [torch.randn(B, n) for n in Ns]
+    st = sv.stream()
+    xd = x.cuda()
+    Wd, bd, gd = [w.cuda() for w in Ws], [b.cuda() for b in bs], [g.cuda() for g in gs]
+    outs = [torch.empty(B, n, device="cuda") for n in Ns]
+    dW, db = [torch.ones(n, K, device="cuda") for n in Ns], [torch.ones(n, device="cuda") for n in Ns]
+    h = Heads()
+    h.n = 3
+    for i in range(3):
+        h.W[i], h.bias[i], h.out[i], h.g[i], h.dW[i], h.dbias[i], h.N[i] = ptr(Wd[i]), ptr(bd[i]), ptr(outs[i]), ptr(gd[i]), ptr(dW[i]), ptr(db[i]), Ns[i]
+    check(lib.sv_heads_fwd(ptr(xd), K, C.byref(h), B, K, st))
+    for i in range(3):
+        assert rel_rms(outs[i], x @ Ws[i].t() + bs[i]) < 1e-5
+        single = torch.empty(B, Ns[i], device="cuda")
+        check(lib.sv_linear_fwd(ptr(xd), K, ptr(Wd[i]), K, 0, ptr(bd[i]), ptr(single), None, Ns[i], None, 0, B, Ns[i], K, st))
+        assert torch.equal(single, outs[i])
+    gx = torch.full((B, K), 3.0, device="cuda")
+    check(lib.sv_heads_bwd_input(C.byref(h), ptr(gx), K, B, K, st))
+    assert rel_rms(gx, sum(g @ w for g, w in zip(gs, Ws))) < 1e-5
+    check(lib.sv_heads_bwd_weight(C.byref(h), ptr(xd), K, B, K, st))
+    for i in range(3):
+        assert rel_rms(dW[i], gs[i].t() @ x + 1) < 1e-5 and rel_rms(db[i], gs[i].sum(0) + 1) < 1e-5
+
+
+def test_wgrad_reduce_batched_equals_single(sv):
+    """sv_wgrad_reduce_batched over several weight tensors (more than one launch's worth of descriptors, ragged n_real / c_real,
+    permuted taps, accumulate semantics) against sv_wgrad_reduce one tensor at a time"""
+    from shotvae_b200._abi import lib, check, ptr, taps_array, ReduceDesc
+    torch.manual_seed(41)
+    st = sv.stream()
+    shapes = [(148, 32, 32, 9, 32, 32), (20, 16, 16, 9, 16, 3), (51, 128, 128, 9, 128, 128), (7, 48, 64, 4, 40, 64), (1, 16, 16, 1, 16, 16)] * 9
+    descs, want, got = [], [], []
+    keep = []
+    for i, (splits, N, Cc, T, n_real, c_real) in enumerate(shapes):
+        part = torch.randn(splits, N, T * Cc, device="cuda")
+        tap = list(reversed(range(T)))
+        g0 = torch.randn(n_real, c_real, T, device="cuda")        # grad[n][c][tap]: sn = c_real*T, sc = T, st = 1
+        a, b = g0.clone(), g0.clone()
+        check(lib.sv_wgrad_reduce(ptr(part), ptr(a), splits, N, Cc, T, n_real, c_real, c_real * T, T, 1, taps_array(tap), st))
+        d = ReduceDesc()
+        d.partial, d.grad, d.sn, d.sc, d.st = ptr(part), ptr(b), c_real * T, T, 1
+        d.splits, d.N, d.C, d.T, d.n_real, d.c_real = splits, N, Cc, T, n_real, c_real
+        for k, v in enumerate(tap):
+            d.tap_index[k] = v
+        descs.append(d)
+        want.append(a)
+        got.append(b)
+        keep.append(part)
+        ref = g0.cpu() + part.sum(0).cpu().view(N, T, Cc)[:n_real, :, :c_real].permute(0, 2, 1).flip(2)
+        assert rel_rms(a, ref) < 1e-5
+    arr = (ReduceDesc * len(descs))(*descs)
+    check(lib.sv_wgrad_reduce_batched(arr, len(descs), st))
+    for a, b in zip(want, got):
+        assert rel_rms(b, a) < 1e-6
+
+
 def test_cpu_tensors_are_refused(sv):
     from lib.criterion import VAECriterion
     with pytest.raises(sv.ShotVaeError):
