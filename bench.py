@@ -307,6 +307,11 @@ def main():
         # (forced: a box-level NCCL_DEBUG=WARN would hide the "comm ... nranks N" lines the driver checks; SHOTVAE_NCCL_DEBUG overrides)
         os.environ["NCCL_DEBUG"] = os.environ.get("SHOTVAE_NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # NCCL on at most 4 SMs; the backward's persistent grids then use the other 144 (ddp.GradReducer.cta_limit).  The
+        # exchange is 51 MB (C2) / 192 MB (C4) per step hidden behind >= 2 ms of backward: bandwidth is not what it needs.
+        # SHOTVAE_NCCL_MAX_CTAS=0 restores NCCL's own choice (24 channels for NVLS all-reduce on 8 GPUs) and full grids.
+        if os.environ.get("SHOTVAE_NCCL_MAX_CTAS", "4") != "0":
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("SHOTVAE_NCCL_MAX_CTAS", "4"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from shot_vae_model.vae import VariationalAutoEncoder
     from shotvae_b200.engine import TrainStep, default_hyper

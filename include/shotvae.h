@@ -33,6 +33,12 @@ const char* sv_last_error(void);
 int sv_has_tcgen05(void);
 /* number of kernel launches issued by this library since process start (bench `gpu_launches`) */
 long long sv_launch_count(void);
+/* Persistent-grid kernels (the tcgen05 convolutions and weight gradients: one CTA per SM, statically strided tiles) launch
+ * at most n CTAs from now on (0 = one per SM).  A data-parallel step sets it around the part of the backward that overlaps the
+ * NCCL all-reduces (replacement of the reference's nn.DataParallel reduce, wideresnet.py:78-94): a collective that holds k SMs
+ * while a 148-CTA grid is launched makes that grid's last k CTAs a second wave, i.e. doubles the kernel's time.  Returns the
+ * previous limit.  The value is read at launch (and at CUDA-graph capture) time. */
+int sv_set_cta_limit(int32_t n);
 
 /* ---- implicit GEMM (replaces every nn.Conv2d / nn.ConvTranspose2d fprop + dgrad call site:
  *      wideresnet.py:12-14,29-35,41-43; preactresnet.py:31-36,56-59; decoder.py:13-58) ------------

@@ -7,6 +7,9 @@
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_cta_limit{0};
+
+int sv_cta_limit() { return g_cta_limit.load(std::memory_order_relaxed); }
 
 void sv_set_error(const char* fmt, ...) {
   va_list ap;
@@ -40,6 +43,11 @@ extern "C" {
 int sv_abi_version(void) { return SV_ABI_VERSION; }
 const char* sv_last_error(void) { return g_err; }
 long long sv_launch_count(void) { return g_launches.load(); }
+int sv_set_cta_limit(int32_t n) {
+  const int old = g_cta_limit.load();
+  g_cta_limit.store(n > 0 ? n : 0);
+  return old;
+}
 int sv_sizeof_igemm_args(void) { return (int)sizeof(sv_igemm_args); }
 int sv_sizeof_wgrad_args(void) { return (int)sizeof(sv_wgrad_args); }
 int sv_sizeof_bn_bwd_term(void) { return (int)sizeof(sv_bn_bwd_term); }

@@ -13,6 +13,7 @@
 
 void sv_set_error(const char* fmt, ...);
 int sv_check_launch(const char* what);
+int sv_cta_limit();          // 0 = every SM; see sv_set_cta_limit
 
 #define SV_REQUIRE(cond, ...)                                                                     \
   do {                                                                                            \

@@ -280,7 +280,8 @@ int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  const int lim = sv_cta_limit();      // sv_set_cta_limit: SMs left to a concurrent collective (data parallel backward)
+  return (lim > 0 && lim < n) ? lim : n;
 }
 
 int ilog2(int v) {

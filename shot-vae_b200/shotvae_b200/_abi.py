@@ -69,6 +69,7 @@ _PROTOS = {
     "sv_last_error": (C.c_char_p, []),
     "sv_has_tcgen05": (C.c_int, []),
     "sv_launch_count": (C.c_longlong, []),
+    "sv_set_cta_limit": (C.c_int, [i32]),
     "sv_sizeof_igemm_args": (C.c_int, []),
     "sv_sizeof_wgrad_args": (C.c_int, []),
     "sv_sizeof_bn_bwd_term": (C.c_int, []),

@@ -13,6 +13,8 @@ Replicas start identical: construction broadcasts rank 0's parameters, BatchNorm
 (nn.DataParallel gets that for free from its single master copy; torch DDP does the same broadcast).
 The per-rank noise streams must differ -- seed the CUDA generator per rank (bench.py does).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -46,6 +48,17 @@ class GradReducer:
                 self.segments.append("enc%d" % i)
             assert sum(e - s for s, e in (self.buckets[k] for k in self.segments)) == split, "encoder segments do not tile the encoder range"
         self.bytes_per_step = net.n_params * 4
+        # SMs left to NCCL while a bucket is in flight.  The tcgen05 conv / weight-gradient kernels are persistent grids with
+        # statically strided tiles, one CTA per SM: if a collective holds k SMs when such a grid starts, its last k CTAs form a
+        # second wave and the kernel takes twice as long (MEASURED at 8 GPUs: 24 NVLS channels, 4.81 -> 5.04 ms/step).  With
+        # NCCL_MAX_CTAS=k in the environment (bench.py / launch.py set it before the communicator exists) NCCL never uses more
+        # than k CTAs, and the engine launches the backward's persistent grids with SMs - k CTAs (sv_set_cta_limit) so that both
+        # always fit.  0 = no reservation.
+        self.reserved_ctas = int(os.environ.get("NCCL_MAX_CTAS", "0") or 0) if self.cuda else 0
+        self.cta_limit = 0
+        if self.reserved_ctas > 0:
+            sms = torch.cuda.get_device_properties(net.grads.device).multi_processor_count
+            self.cta_limit = max(sms - self.reserved_ctas, sms // 2)
         if broadcast:
             self.broadcast_state()
 

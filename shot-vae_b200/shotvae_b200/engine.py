@@ -214,15 +214,21 @@ class TrainStep:
         the encoder, plan.Net.bwd_segments); 2 = SGD + BatchNorm running statistics.
         With several ranks the parts are separate CUDA graphs and the bucket all-reduces are issued between
         them on a side stream (NCCL is kept out of the captured graphs)."""
+        # data parallel: the backward overlaps the bucket all-reduces -> its persistent grids leave NCCL's SMs alone (ddp.py)
+        limit = self.reducer.cta_limit if self.reducer is not None else 0
         for part in parts:
             if part == 0:
                 self._part0()
-            elif part == 1:
-                self._part1()
             elif part == 2:
                 self._part2()
             else:
-                self._part1(seg=part[1])
+                if limit:
+                    lib.sv_set_cta_limit(limit)
+                try:
+                    self._part1(seg=None if part == 1 else part[1])
+                finally:
+                    if limit:
+                        lib.sv_set_cta_limit(0)
 
     def _ddp_plan(self):
         """[(parts of one CUDA graph, bucket to all-reduce after it)] for a data-parallel step"""
@@ -330,6 +336,19 @@ class TrainStep:
                                            ptr(self.m_mu), ptr(self.m_sig), ptr(self.coef[8:]), B, D, nd, ptr(self.terms[8:]),
                                            ptr(g_la2[B:]), ptr(g_mu2[B:]), ptr(g_ls2[B:]), 0, st))
             # (the backward of [P2 | P4] -- heads + encoder only -- runs together with [P1 | P3] in part 1)
+        # The decoder forwards of P2 / P4 (kept only for their BatchNorm running statistics) need nothing but [P2 | P4]'s heads.
+        # With the two encoder forwards overlapped, the sample -> decoder -> ELBO -> decoder-backward chain of [P1 | P3] is the
+        # ONLY chain in flight from here to part 1 (timeline: ~650 us with one kernel at a time, profiles/r02_step_timeline.md):
+        # the dead forwards fill it instead of competing with the encoder backward.  SHOTVAE_DEAD_EARLY=0: beside part 1.
+        self._dead_done = False
+        if conc and not self.skip_dead_decoders and os.environ.get("SHOTVAE_DEAD_EARLY", "1") != "0":
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side2.wait_event(ev)
+            with torch.cuda.stream(self.side2):
+                self._dead_decoders()
+            main.wait_stream(self.side2)
+            self._dead_done = True
         if side is not None:
             main.wait_stream(side)
 
@@ -347,7 +366,7 @@ class TrainStep:
             net.encoder_bwd(S, None, seg=seg)
             return
         g_mu, g_ls, g_la = self._g
-        dead = (not self.m2) and (not self.skip_dead_decoders)
+        dead = (not self.m2) and (not self.skip_dead_decoders) and not getattr(self, "_dead_done", False)
         main = torch.cuda.current_stream()
         if dead and self.side2 is not None:
             ev = torch.cuda.Event()

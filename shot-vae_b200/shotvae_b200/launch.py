@@ -31,6 +31,8 @@ def init_distributed():
     if world > 1:
         import torch.distributed as dist
         if not dist.is_initialized():
+            # NCCL on at most 4 SMs, the backward's persistent grids on the others (ddp.GradReducer.cta_limit)
+            os.environ.setdefault("NCCL_MAX_CTAS", "4")
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         torch.cuda.manual_seed(1234 + rank)          # per-rank device noise (eps / gumbel draws)
     return rank, world, local

@@ -27,6 +27,7 @@ def _worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     torch.cuda.set_device(rank)
+    os.environ["NCCL_MAX_CTAS"] = "4"               # the reserved-SM path: backward grids of 144 CTAs (ddp.GradReducer.cta_limit)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from shotvae_b200.engine import TrainStep
     from shotvae_b200.ddp import GradReducer
