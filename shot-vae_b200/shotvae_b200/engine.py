@@ -57,6 +57,7 @@ class TrainStep:
         self.use_graph, self.device_noise = use_graph, device_noise
         self.skip_dead_decoders = skip_dead_decoders
         self.reducer = reducer
+        self.cta_limit = getattr(reducer, "cta_limit", 0) if reducer is not None else 0
         # Data parallel: one CUDA graph per backward segment, the NCCL calls issued between them from the host.
         # SHOTVAE_DDP_GRAPH=single captures the all-reduces into ONE graph instead (works: NCCL supports stream capture) --
         # MEASURED at 2 GPUs: 5.005 vs 5.021 ms/step, i.e. the host-side gaps are not what the 2 % data-parallel overhead is made
@@ -215,7 +216,7 @@ class TrainStep:
         With several ranks the parts are separate CUDA graphs and the bucket all-reduces are issued between
         them on a side stream (NCCL is kept out of the captured graphs)."""
         # data parallel: the backward overlaps the bucket all-reduces -> its persistent grids leave NCCL's SMs alone (ddp.py)
-        limit = self.reducer.cta_limit if self.reducer is not None else 0
+        limit = self.cta_limit        # (fixed at construction: the per-launch argument records are built for this grid size)
         for part in parts:
             if part == 0:
                 self._part0()
