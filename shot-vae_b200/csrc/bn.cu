@@ -93,44 +93,64 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const TA* __restrict__ 
   }
 }
 
-// BatchNorm finalize fused into the apply: every thread derives scale/shift of its 8 channels from the raw
-// (sum, sum^2) statistics; block (0, g) also publishes mean / var / scale / shift for the backward pass and
-// the running-statistics update.  Saves one launch per BatchNorm.
+// BatchNorm finalize fused into the apply: the block derives scale / shift of its C channels ONCE from the raw (sum, sum^2)
+// statistics (FP64 mean / variance, two divisions per channel) into shared memory -- round 2 had every THREAD do that for its
+// 8 channels: 16 double divisions x 256 threads x ~600 blocks per launch, about 4 us of FP64 pipe time in an 11 us kernel --
+// while the first rows of y are already in flight; block (0, g) also publishes mean / var / scale / shift for the backward pass
+// and the running-statistics update.  Saves one launch per BatchNorm.
 template <typename TA>
 __global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(const TA* __restrict__ y, TA* __restrict__ a,
                                                                   const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, float count, float eps, float slope,
                                                                   long long rows_per_group, long long slab_rows, int C, float* mean,
                                                                   float* var, float* scale, float* shift) {
+  __shared__ float s_sc[2048], s_sh[2048];      // C <= 2048 (C / 8 <= 256 chunks per row)
   pdl_trigger();
   pdl_wait();
   const int cpr = C / 8;
   const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
   const int g = blockIdx.y;
-  float sc[8], sh[8];
+  const long long r0 = (long long)blockIdx.x * slab_rows;
+  const long long r1 = min(r0 + slab_rows, rows_per_group);
+  constexpr int U = 4;
+  typename V8<TA>::raw q[U];
+  // first rows of this thread: in flight while the coefficients are computed
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = chunk * 8 + j;
+  for (int u = 0; u < U; ++u) {
+    const long long r = r0 + rl + (long long)u * nrl;
+    if (r < r1) q[u] = V8<TA>::load(y + ((size_t)g * rows_per_group + r) * C + chunk * 8);
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double s1 = stats[(size_t)(g * 2 + 0) * C + c], s2 = stats[(size_t)(g * 2 + 1) * C + c];
     const double dm = s1 / count;
     double dv = s2 / count - dm * dm;
     if (dv < 0.0) dv = 0.0;
     const float m = (float)dm, v = (float)dv;
-    sc[j] = gamma[c] * rsqrtf(v + eps);
-    sh[j] = beta[c] - m * sc[j];
-    if (blockIdx.x == 0 && rl == 0) {
+    const float sc = gamma[c] * rsqrtf(v + eps);
+    const float sh = beta[c] - m * sc;
+    s_sc[c] = sc;
+    s_sh[c] = sh;
+    if (blockIdx.x == 0) {
       const size_t k = (size_t)g * C + c;
-      mean[k] = m; var[k] = v; scale[k] = sc[j]; shift[k] = sh[j];
+      mean[k] = m; var[k] = v; scale[k] = sc; shift[k] = sh;
     }
   }
-  const long long r0 = (long long)blockIdx.x * slab_rows;
-  const long long r1 = min(r0 + slab_rows, rows_per_group);
-  constexpr int U = 4;
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s_sc[chunk * 8 + j];
+    sh[j] = s_sh[chunk * 8 + j];
+  }
   for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
-    typename V8<TA>::raw q[U];
+    typename V8<TA>::raw cur[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = q[u];
+    // next batch of rows in flight while this one is transformed and stored
+    const long long rn = rb + (long long)nrl * U;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = rb + (long long)u * nrl;
+      const long long r = rn + (long long)u * nrl;
       if (r < r1) q[u] = V8<TA>::load(y + ((size_t)g * rows_per_group + r) * C + chunk * 8);
     }
 #pragma unroll
@@ -138,7 +158,7 @@ __global__ void __launch_bounds__(256) bn_finalize_act_fwd_kernel(const TA* __re
       const long long r = rb + (long long)u * nrl;
       if (r < r1) {
         float v[8];
-        V8<TA>::unpack(q[u], v);
+        V8<TA>::unpack(cur[u], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float t = fmaf(v[j], sc[j], sh[j]);
@@ -353,6 +373,8 @@ __global__ void __launch_bounds__(256, (NT == 1 && sizeof(TA) == 2) ? 2 : 1) bn_
   const long long r0 = (long long)blockIdx.x * slab_rows;
   const long long r1 = min(r0 + slab_rows, rows_per_group);
   constexpr int U = 4;      // rows in flight per thread
+  // (MEASURED, not kept: requesting the first rows before the per-channel coefficients are fetched -- C4 2.06 -> 2.83 ms of
+  // bn_bwd_apply per step: the 12 extra live vectors cost more than the ~1 us of exposed latency)
   for (long long rb = r0 + rl; rb < r1; rb += (long long)nrl * U) {
     typename V8<TA>::raw yq[U], aq[U], gq[NT][U];
 #pragma unroll

@@ -17,6 +17,8 @@ for c in c3 c4 c5; do
   python tools/bench_line.py $c $O/${T}_bench_$c.json
 done
 timeout 300 python bench.py --kernels > $O/${T}_bandwidth_kernels.json 2> $O/${T}_bandwidth_kernels.err
+# kernel timeline of one CUDA-graph replay (CUPTI through torch.profiler): what runs beside what, gaps on the critical chain
+for c in c2 c4; do timeout 300 python tools/step_timeline.py $c ${T}_$c > $O/${T}_timeline_$c.txt 2>&1; done
 kill $SMI
 if [ -z "$NO_NCU" ]; then
   # launch list: eager (--no-graph) so that launch order = program order; skip the build-up steps
