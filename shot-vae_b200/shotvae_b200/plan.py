@@ -26,6 +26,7 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 # SHOTVAE_FUSE_BNBWD=0: BatchNorm-backward statistics by the separate sv_bn_bwd_reduce pass everywhere (A/B switch)
 FUSE_BN_BWD = os.environ.get("SHOTVAE_FUSE_BNBWD", "1") != "0"
+BWD_DECOUPLE = os.environ.get("SHOTVAE_BWD_DECOUPLE", "0") != "0"      # MEASURED: 4.69-4.71 vs 4.66-4.71 ms/step (C2), 24.2 vs 24.4 (C4) -- no gain, off
 WG_WORKSPACE_FLOATS = 24 * 1024 * 1024          # cap of one weight tensor's partial-sum workspace
 # queued reductions are issued once their partial sums exceed this (about half of the 126 MB L2: the reduction should still hit)
 WG_FLUSH_BYTES = int(os.environ.get("SHOTVAE_WG_FLUSH_MB", "64")) * (1 << 20)
@@ -698,8 +699,12 @@ class Net:
                 self._igemm(ctx, k + ".conv2.d", g_out, k + ".conv2.d00", NB, Ho, Ho, Ho, Ho, out=g_a2)
             on_side(lambda: self._wgrad(ctx, k + ".conv2.w", rec["a2"], g_out, conv_taps(3, 1), NB, Ho, Ho, u.cout, Ho, Ho, u.cout, 1,
                                         u.prefix + ".f_block.conv2.weight", u.cout, u.cout, u.cout * K9, K9, 1), ev)
-            g_y1 = ctx.t("g.y1.%d.%d" % (Ho, u.cout), (NB, Ho, Ho, u.cout))
-            if side_done is not None:
+            # g.y1 and the unit's input gradient are PER-UNIT buffers (round 2 late): with buffers shared by shape the main
+            # stream had to wait for the previous unit's weight gradients before overwriting what they read, which locked the
+            # dgrad -> BatchNorm-backward chain to the weight-gradient stream unit by unit (gaps of 25-50 us on the critical
+            # chain wherever the weight gradient was the slower one).  SHOTVAE_BWD_DECOUPLE=0: shared buffers + the wait.
+            g_y1 = ctx.t(("g.y1.%s" % k) if BWD_DECOUPLE else "g.y1.%d.%d" % (Ho, u.cout), (NB, Ho, Ho, u.cout))
+            if side_done is not None and not BWD_DECOUPLE:
                 main.wait_event(side_done)      # the previous unit's conv1 weight gradient has read g.y1 / its g_out
             self._bn_bwd(ctx, k + ".bn2", [dict(rec=rec["bn2"], g_a=g_a2, slope=slope, fused=f2)], rec["y1"], None, g_y1, rows_out, Ho * Ho)
 
@@ -725,7 +730,7 @@ class Net:
                 terms.append(dict(rec=rec["bns"], g_a=g_as, slope=sslope, fused=fs))
                 addend = None
             flip ^= 1
-            g_prev = ctx.t("g.h.%d.%d.%d" % (Hin, u.cin, flip), (NB, Hin, Hin, u.cin))
+            g_prev = ctx.t(("g.h.%s" % k) if BWD_DECOUPLE else "g.h.%d.%d.%d" % (Hin, u.cin, flip), (NB, Hin, Hin, u.cin))
             self._bn_bwd(ctx, k + ".bn1", terms, rec["h_in"], addend, g_prev, rows_in, Hin * Hin)
             g_h = g_prev
         if side is not None:

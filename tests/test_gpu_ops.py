@@ -207,6 +207,39 @@ def test_conv_wgrad_benchmark_batch_matches_autograd(sv, cin, cout, H, k):
     assert rel_rms(grad.cpu(), w.grad) < 2e-3
 
 
+@pytest.mark.parametrize("cin,cout,H,k", [(32, 32, 32, 3), (64, 64, 16, 3), (128, 128, 8, 3)])
+def test_cta_limit_leaves_results_unchanged(sv, cin, cout, H, k):
+    """sv_set_cta_limit (the data-parallel backward leaves NCCL's SMs alone, ddp.GradReducer.cta_limit): the persistent conv
+    and weight-gradient grids launched on fewer CTAs than SMs give the same convolution bit for bit (tile striding only)
+    and the same weight gradient up to the summation order over the per-CTA partial sums"""
+    from shotvae_b200.plan import conv_taps
+    from shotvae_b200._abi import lib
+    NB = 256
+    torch.manual_seed(5 + cin + H)
+    x, w = bf(torch.randn(NB, cin, H, H)), bf(torch.randn(cout, cin, k, k) * 0.1)
+    g = bf(torch.randn(NB, cout, H, H) * 0.1)
+    taps = conv_taps(k, k // 2)
+    impl = 3 if cin < 128 else 0
+    Wt = pack(sv, w, cout, cin, taps, cout, cin, cin * k * k, k * k, 1, impl)
+    xa, ga = nhwc(x), nhwc(g).view(-1, cout)
+    outs, grads = [], []
+    try:
+        for limit in (0, 144, 37):
+            assert lib.sv_set_cta_limit(limit) in (0, 144, 37)
+            out = torch.empty(NB, H, H, cout, dtype=torch.bfloat16, device="cuda")
+            igemm(sv, xa, Wt, taps, NB, H, H, cin, H, H, cout, out=out, impl=impl)
+            grad = torch.zeros(cout, cin, k, k, device="cuda")
+            wgrad(sv, xa, ga, taps, NB, H, H, cin, H, H, cout, 1, grad, cout, cin, cin * k * k, k * k, 1, 1, 2)
+            torch.cuda.synchronize()
+            outs.append(out)
+            grads.append(grad)
+    finally:
+        lib.sv_set_cta_limit(0)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert rel_rms(grads[1], grads[0]) < 1e-5 and rel_rms(grads[2], grads[0]) < 1e-5
+    assert rel_rms(from_nhwc(outs[0]), F.conv2d(x, w, None, 1, k // 2)) < 4e-3
+
+
 @pytest.mark.parametrize("impl", [0, 2])
 @pytest.mark.parametrize("cin,cout,Hin,NB", [(1024, 512, 1, 16), (512, 256, 2, 8), (256, 128, 4, 8), (128, 64, 8, 4)])
 def test_convT_phases_in_one_grid_equal_separate_launches(sv, impl, cin, cout, Hin, NB):
