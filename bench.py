@@ -7,8 +7,10 @@ A "step" is one pass of the hot path -- the loop body of main_shot_vae.train (:2
 forwards, 2 backwards, SGD -- over one (labelled 128, unlabelled 128) synthetic batch pair per GPU.
 Prints ONE JSON line (rank 0).  `value` is images/s with the inputs already resident in HBM
 (CUDA-graph replay of the whole step); `e2e` is the same metric through the public call
-`TrainStep.step(host tensors)`: pinned-host -> device copies of the batch + the host RNG draws, the
-step, and a device -> host read of the loss terms, every step.  `roofline` describes the dominant
+`TrainStep.step_async(host tensors)`: every step the batch + the host RNG draws are copied pinned-host -> device
+(on a copy stream, beside the previous step), the step runs, and its loss terms are read device -> host (returned
+by the NEXT call: the host is never more than one step ahead; `--e2e-sync` times `TrainStep.step`, the same work
+with a host synchronisation per step: `e2e.sync_ms_per_step`).  `roofline` describes the dominant
 kernel family (the implicit-GEMM convolution kernel), timed with CUDA events around each launch in
 an instrumented eager replay of the same launch sequence.  `cpu_baseline` / `--impl reference` time the UNMODIFIED
 reference's own `train()` (baseline/_ref, driven by baseline/ref_harness.py in a subprocess: FP32 ATen kernels on this
@@ -255,6 +257,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c2")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--e2e-sync", action="store_true", help="e2e through TrainStep.step (host sync per step) instead of step_async")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--dump-kernels", default="")
     ap.add_argument("--kernels", action="store_true", help="time the bandwidth-bound kernels alone (B = 16384 and B = 128)")
@@ -363,22 +366,36 @@ def main():
     windows.append((w0, time.time()))
     t_res = ev0.elapsed_time(ev1) / 1e3
     log("resident region done")
-    # ---- timed region 2: end to end through TrainStep.step(host tensors) -----------------------------
-    sync_all()
-    w0 = time.time()
-    ev0.record()
-    last = None
-    for i in range(a.steps):
-        last = ts.step(*pool[i % len(pool)])
-    ev1.record()
-    sync_all()
-    windows.append((w0, time.time()))
-    t_e2e = ev0.elapsed_time(ev1) / 1e3
+    # ---- timed region 2: end to end through the public call, host tensors in, loss terms out, every step ----------
+    def e2e_region(pipelined):
+        sync_all()
+        w0 = time.time()
+        ev0.record()
+        last = None
+        for i in range(a.steps):
+            if pipelined:
+                last = ts.step_async(*pool[i % len(pool)]) or last
+            else:
+                last = ts.step(*pool[i % len(pool)])
+        if pipelined:
+            last = ts.drain()            # the last step's terms: inside the timed region
+        ev1.record()
+        sync_all()
+        windows.append((w0, time.time()))
+        return ev0.elapsed_time(ev1) / 1e3, last
+
+    t_e2e_sync, last = e2e_region(False)             # TrainStep.step: copy, step, read, host sync -- every step
+    t_e2e = t_e2e_sync
+    if not a.e2e_sync:
+        for i in range(3):                           # builds the staging slots / copy stream outside the timed region
+            ts.step_async(*pool[i % len(pool)])
+        ts.drain()
+        t_e2e, last = e2e_region(True)               # TrainStep.step_async: the same, copies beside the previous step
     log("e2e region done")
     if world > 1:
-        tt = torch.tensor([t_res, t_e2e], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_res, t_e2e, t_e2e_sync], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_res, t_e2e = float(tt[0]), float(tt[1])
+        t_res, t_e2e, t_e2e_sync = float(tt[0]), float(tt[1]), float(tt[2])
     clocks = sampler.summary(windows) if sampler else None
     launches = (ts.launches_per_step or 0)
 
@@ -461,8 +478,12 @@ def main():
     imgs = world * BATCH * a.steps
     line = dict(base, impl="ours", value=imgs / t_res, steps=a.steps, warmup=W, ms_per_step=1e3 * t_res / a.steps, dtype="bf16",
                 clocks=clocks, gpu_launches=launches * a.steps,
-                e2e=dict(value=imgs / t_e2e, unit="images/s", h2d_bytes_per_step=ts.h2d_bytes(), d2h_bytes_per_step=64,
-                         ms_per_step=1e3 * t_e2e / a.steps),
+                e2e=dict(value=imgs / t_e2e, unit="images/s",
+                         h2d_bytes_per_step=ts.h2d_bytes() if a.e2e_sync else ts.h2d_bytes_async(), d2h_bytes_per_step=64,
+                         ms_per_step=1e3 * t_e2e / a.steps,
+                         api="TrainStep.step (host sync per step)" if a.e2e_sync else
+                             "TrainStep.step_async (batch k+1 copied on a copy stream beside step k; terms of step k returned by call k+1; drain() at the end)",
+                         sync_ms_per_step=1e3 * t_e2e_sync / a.steps),
                 roofline=roof, cpu_baseline=cpu, gpu_reference=gpu_ref)
     line["details"] = dict(parallelism="dp%d" % world, cuda_graph=bool(ts.graph is not None), launches_per_step=launches,
                            noise="device RNG (torch CUDA generator); lambda / pairing drawn on the host as in the reference",

@@ -72,11 +72,15 @@ class TrainStep:
         self.dev = dev
         f32, i64 = torch.float32, torch.int64
         z = lambda *s, dtype=f32: torch.zeros(*s, dtype=dtype, device=dev)
-        # static device inputs
-        self.img_l, self.img_u = z(B, net.in_ch, 32, 32), z(B, net.in_ch, 32, 32)
-        self.label_l, self.label_u = z(B, dtype=i64), z(B, dtype=i64)
-        self.lam = z(4)                                  # {lam_l, 1-lam_l, lam_u, 1-lam_u}
-        self.idx_l, self.idx_u, self.s_lab = z(B, dtype=i64), z(B, dtype=i64), z(B, dtype=i64)
+        # static device inputs: views of ONE arena, so that the pipelined end-to-end path (step_async) moves a step's inputs
+        # with one host -> device and one device -> device copy
+        self._in_layout = [("img_l", (B, net.in_ch, 32, 32), f32), ("img_u", (B, net.in_ch, 32, 32), f32), ("label_l", (B,), i64),
+                           ("label_u", (B,), i64), ("lam", (4,), f32),       # lam = {lam_l, 1-lam_l, lam_u, 1-lam_u}
+                           ("idx_l", (B,), i64), ("idx_u", (B,), i64), ("s_lab", (B,), i64)]
+        self._in_arena, iv = self._input_arena(lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
+        self.img_l, self.img_u, self.label_l, self.label_u = iv["img_l"], iv["img_u"], iv["label_l"], iv["label_u"]
+        self.lam, self.idx_l, self.idx_u, self.s_lab = iv["lam"], iv["idx_l"], iv["idx_u"], iv["s_lab"]
+        self._pipe = None            # step_async state (staging slots, copy stream), built on first use
         self.eps, self.unif = z(4, B, D), z(2, B, nd)
         # device-resident scalars
         self.coef = z(16)
@@ -118,6 +122,16 @@ class TrainStep:
         self.set_epoch(0)
         self.set_lr(self.h["lr"])
         net.zero_grads()
+
+    def _input_arena(self, alloc):
+        """one byte arena holding every per-step input in self._in_layout (16-byte aligned fields) -> (arena, {name: typed view})"""
+        offs, off = [], 0
+        for name, shape, dt in self._in_layout:
+            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            offs.append((name, shape, dt, off, n))
+            off += (n + 15) // 16 * 16
+        arena = alloc(off)
+        return arena, {name: arena[o:o + n].view(dt).view(shape) for name, shape, dt, o, n in offs}
 
     # ---- schedules ---------------------------------------------------------------------------
     def set_epoch(self, epoch):
@@ -494,10 +508,78 @@ class TrainStep:
         self.run_resident()
         return self.read_terms()
 
+    # ---- pipelined end-to-end path -------------------------------------------------------------------------------
+    def step_async(self, image_l, label_l, image_u, label_u, draws="auto"):
+        """Pipelined end-to-end call (host batch in, loss terms out, one call per optimizer step like step()): this batch's
+        inputs and host draws go through a pinned staging slot to a device staging slot on a COPY stream -- beside the previous
+        step, which is still running -- and the step is enqueued behind one device-to-device copy.  Returns the loss terms of the
+        PREVIOUS call (None on the first): the host never waits for the step it has just enqueued, and is never more than one
+        step ahead.  drain() returns the terms of the last step.  (step() is the same work with a host synchronisation per step:
+        copy, step, read.)"""
+        if self._pipe is None:
+            mk_h = lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory()
+            mk_d = lambda n: torch.zeros(n, dtype=torch.uint8, device=self.dev)
+            self._pipe = dict(host=[self._input_arena(mk_h) for _ in range(2)], dev=[mk_d(self._in_arena.numel()) for _ in range(2)],
+                              copy=torch.cuda.Stream(device=self.dev), k=0, pending=None,
+                              h2d=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)],
+                              done=[torch.cuda.Event() for _ in range(2)], used=[False, False],
+                              terms=[torch.zeros(16).pin_memory() for _ in range(2)])
+        P = self._pipe
+        slot = P["k"] & 1
+        harena, hv = P["host"][slot]
+        if P["used"][slot]:
+            P["h2d"][slot].synchronize()            # the slot's previous host -> device copy (two calls ago) has left the host buffer
+        hv["img_l"].copy_(image_l)
+        hv["img_u"].copy_(image_u)
+        hv["label_l"].copy_(label_l)
+        hv["label_u"].copy_(label_u)
+        d = self.draw_host() if draws == "auto" else draws
+        if d is not None:
+            lam_l, idx_l, lam_u, idx_u = d
+            hv["lam"].copy_(torch.tensor([lam_l, 1 - lam_l, lam_u, 1 - lam_u], dtype=torch.float64).float())
+            hv["idx_l"].copy_(idx_l)
+            hv["idx_u"].copy_(idx_u)               # (--om: recomputed on the device inside the step)
+            hv["s_lab"].copy_(hv["label_l"][idx_l])          # smoothed_disc_label = disc_label[index] (mixup.py:37)
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(P["copy"]):
+            if P["used"][slot]:
+                P["copy"].wait_event(P["free"][slot])        # the device slot was consumed by the step two calls ago
+            P["dev"][slot].copy_(harena, non_blocking=True)
+            P["h2d"][slot].record(P["copy"])
+        main.wait_event(P["h2d"][slot])
+        self._in_arena.copy_(P["dev"][slot], non_blocking=True)
+        P["free"][slot].record(main)
+        P["used"][slot] = True
+        self.run_resident()
+        P["terms"][slot].copy_(self.terms, non_blocking=True)
+        P["done"][slot].record(main)
+        prev, P["pending"] = P["pending"], slot
+        P["k"] += 1
+        return None if prev is None else self._collect(prev)
+
+    def drain(self):
+        """loss terms of the last step_async() call (waits for it); None when nothing is pending"""
+        P = self._pipe
+        if P is None or P["pending"] is None:
+            return None
+        slot, P["pending"] = P["pending"], None
+        return self._collect(slot)
+
+    def _collect(self, slot):
+        P = self._pipe
+        P["done"][slot].synchronize()
+        return self._terms_dict(P["terms"][slot])
+
+    def h2d_bytes_async(self):
+        return int(self._in_arena.numel())
+
     def read_terms(self):
         self.h_terms.copy_(self.terms, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        t = {k: float(self.h_terms[i]) for i, k in enumerate(TERM_NAMES)}
+        return self._terms_dict(self.h_terms)
+
+    def _terms_dict(self, h_terms):
+        t = {k: float(h_terms[i]) for i, k in enumerate(TERM_NAMES)}
         s = self.sched
         for sfx in ("l", "u"):
             t["prior_" + sfx] = s["kbc"] * abs(t["klc_" + sfx] - s["cmi"]) + s["kbd"] * abs(t["kld_" + sfx] - s["dmi"])

@@ -354,6 +354,52 @@ def test_engine_graph_replay_equals_eager_sequence():
     assert errs["all"] < 2e-2 and errs["decoder"] < 2e-2 and errs["heads"] < 5e-2, errs
 
 
+@pytest.mark.parametrize("om", [False, True])
+def test_step_async_equals_step(om):
+    """TrainStep.step_async (inputs staged through pinned / device slots on a copy stream, terms returned one call late)
+    is the same computation as TrainStep.step: different batches every step so that a slot mix-up cannot go unnoticed;
+    terms of step k come back from call k + 1, the last from drain()"""
+    from oracle import shotvae_oracle as O
+    from shotvae_b200.engine import TrainStep
+    net, nd, B, steps = "wideresnet-10-1", 10, 16, 6
+    hyper = dict(O.default_hyper("Cifar10"), om=om)
+    st = O.init_state(net, nd)
+    batches = [O.synthetic_batch(B, nd, 3 + i) for i in range(3)]
+    res = []
+    for pipelined in (False, True):
+        model = build_model(net, nd, st).train()
+        ts = TrainStep(model, B, hyper=hyper, use_graph=True, device_noise=False)
+        ts.set_epoch(200)
+        g = torch.Generator().manual_seed(1)
+        terms = []
+        for i in range(steps):
+            ts.set_noise(torch.randn(4, B, 128, generator=g).cuda(), torch.rand(2, B, nd, generator=g).cuda())
+            draws = (0.9 + 0.01 * i, torch.randperm(B, generator=g), 0.3 + 0.1 * i, torch.arange(B) if om else torch.randperm(B, generator=g))
+            il, ll, iu, lu = batches[i % 3]
+            if pipelined:
+                t = ts.step_async(il, ll, iu, lu, draws=draws)
+                assert (t is None) == (i == 0)
+                if t is not None:
+                    terms.append(t)
+            else:
+                terms.append(ts.step(il, ll, iu, lu, draws=draws))
+        if pipelined:
+            terms.append(ts.drain())
+            assert ts.drain() is None
+        assert len(terms) == steps
+        res.append((terms, {k: v.clone() for k, v in model.state_dict().items()}))
+    (t0, s0), (t1, s1) = res
+    for i, (a, b) in enumerate(zip(t0, t1)):
+        for k in ("rec_l", "klc_l", "rec_u", "klc_u", "disc_post_u"):
+            tol = 1e-3 if i == 0 else 2e-2          # (atomics' summation order, amplified by the bf16 network after step 0)
+            assert abs(a[k] - b[k]) <= tol * abs(a[k]), (i, k, a[k], b[k])
+    # the three batches give clearly different reconstruction terms: a stale or swapped staging slot would show here
+    assert abs(t0[0]["rec_l"] - t0[1]["rec_l"]) > 1e-3 * abs(t0[0]["rec_l"])
+    upd = {k: s1[k].float() for k in s0 if s0[k].dtype == torch.float32 and "running" not in k}
+    errs = grad_errors(upd, {k: s0[k].float() for k in upd})
+    assert errs["all"] < 2e-2, errs
+
+
 def test_wrn28x10_forward_and_engine_run():
     """C4 backbone (widths 160/320/640: generic kernels, outside the halo kernel's power-of-two planes)"""
     from oracle import shotvae_oracle as O
