@@ -163,6 +163,19 @@ int sv_igemm_fprop_batch(const sv_igemm_args* args, int32_t n, void* stream) {
     if (same && n > 1) return igemm_fprop_tc_batch(ps, n, (cudaStream_t)stream);
   }
 #endif
+  if (n > 1 && n <= 4) {
+    // ... or when every problem lands on the mma.sync kernel with the same geometry (last decoder layer: 64 -> 3 channels)
+    IgemmParams ps[4];
+    bool same = true;
+    for (int i = 0; i < n && same; ++i) {
+      if (fill_params(&args[i], ps[i]) != SV_OK) return SV_ERR_ARG;
+      int impl = args[i].impl;
+      if (impl == 0) impl = select_impl(ps[i]);
+      same = impl == 1 && ps[i].bn_y == nullptr && ps[i].w_layout == 0 && ps[i].NB == ps[0].NB && ps[i].H == ps[0].H && ps[i].W == ps[0].W && ps[i].C == ps[0].C &&
+             ps[i].N == ps[0].N && ps[i].OH == ps[0].OH && ps[i].OW == ps[0].OW && ps[i].T == ps[0].T && ps[i].w_layout == ps[0].w_layout;
+    }
+    if (same) return igemm_fprop_mma_batch(ps, n, (cudaStream_t)stream);
+  }
   for (int i = 0; i < n; ++i) {
     const int rc = sv_igemm_fprop(&args[i], stream);
     if (rc != SV_OK) return rc;

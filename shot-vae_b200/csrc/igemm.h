@@ -57,6 +57,7 @@ struct WgradParams {
 };
 
 int igemm_fprop_mma(const IgemmParams& p, cudaStream_t st);
+int igemm_fprop_mma_batch(const IgemmParams* batch, int nb, cudaStream_t st);   // same-geometry problems, one grid
 int igemm_wgrad_mma(const WgradParams& p, cudaStream_t st);
 // tcgen05 + TMA path (igemm_tc.cu). Returns SV_ERR_UNSUPPORTED when the shape is not covered.
 bool igemm_fprop_tc_supported(const IgemmParams& p);

@@ -30,9 +30,7 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint
 // fprop-like gather GEMM
 // ------------------------------------------------------------------------------------------------
 template <int BN, int BK>
-__global__ void __launch_bounds__(256) igemm_fprop_mma_kernel(const IgemmParams p) {
-  pdl_trigger();
-  pdl_wait();
+__device__ __forceinline__ void fprop_mma_body(const IgemmParams& p) {
   constexpr int BM = 128, STAGES = 3, LDS = BK + 8, CPR = BK / 8;
   constexpr int WARPS_N = (BN >= 64) ? 2 : 1;
   constexpr int WARPS_M = 8 / WARPS_N;
@@ -223,6 +221,43 @@ __global__ void __launch_bounds__(256) igemm_fprop_mma_kernel(const IgemmParams 
       atomicAdd(&p.stats[(size_t)(g * 2 + 1) * p.N + n0 + tid], s_stat[1][tid]);
     }
   }
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(256) igemm_fprop_mma_kernel(const __grid_constant__ IgemmParams p) {
+  pdl_trigger();
+  pdl_wait();
+  fprop_mma_body<BN, BK>(p);
+}
+
+// up to four problems of identical geometry in one grid (blockIdx.z = problem): the output-parity phases of a transposed
+// convolution whose shape the tcgen05 kernels do not cover (the last decoder layer, 64 -> 3 channels)
+struct MmaBatch {
+  IgemmParams p[4];
+};
+template <int BN, int BK>
+__global__ void __launch_bounds__(256) igemm_fprop_mma_batched_kernel(const __grid_constant__ MmaBatch b) {
+  pdl_trigger();
+  pdl_wait();
+  fprop_mma_body<BN, BK>(b.p[blockIdx.z]);
+}
+
+template <int BN, int BK>
+int launch_fprop_batch(const IgemmParams* ps, int n, cudaStream_t st) {
+  constexpr int BM = 128, STAGES = 3, LDS = BK + 8;
+  constexpr size_t pipe = (size_t)STAGES * (BM + BN) * LDS * sizeof(bf16);
+  constexpr size_t epi = (size_t)BM * (BN + 8) * sizeof(float);
+  constexpr size_t smem = pipe > epi ? pipe : epi;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(igemm_fprop_mma_batched_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  MmaBatch b;
+  for (int i = 0; i < n; ++i) b.p[i] = ps[i];
+  dim3 grid(ceil_div(ps[0].M, BM), ceil_div(ps[0].N, BN), n);
+  sv_launch_pdl(igemm_fprop_mma_batched_kernel<BN, BK>, dim3(grid), dim3(256), smem, st, b);
+  return sv_check_launch("igemm_fprop_mma_batched");
 }
 
 template <int BN, int BK>
@@ -527,13 +562,24 @@ extern "C" int sv_pack_weights_batched(const void* table_dev, int32_t n_packs, i
   return sv_check_launch("pack_weights_batched");
 }
 
-int igemm_fprop_mma(const IgemmParams& p, cudaStream_t st) {
+int igemm_fprop_mma_any(const IgemmParams& p, const IgemmParams* batch, int nb, cudaStream_t st);
+
+int igemm_fprop_mma(const IgemmParams& p, cudaStream_t st) { return igemm_fprop_mma_any(p, nullptr, 0, st); }
+
+// batch[0..nb): problems of the same geometry (NB, H, W, C, N, OH, OW, T) -> one grid
+int igemm_fprop_mma_batch(const IgemmParams* batch, int nb, cudaStream_t st) { return igemm_fprop_mma_any(batch[0], batch, nb, st); }
+
+int igemm_fprop_mma_any(const IgemmParams& p, const IgemmParams* batch, int nb, cudaStream_t st) {
   const bool k32 = (p.C % 32) == 0;
   const int N = p.N;
   // long reductions (the decoder's input-gradient GEMMs: K = taps x C up to 4096) are latency bound on the number of
   // pipeline steps: 64-channel k-blocks halve them
   const bool k64 = (p.C % 64) == 0 && p.T * p.C >= 1024;
 #define SV_DISPATCH(BNV)                                                     \
+  if (batch != nullptr) {                                                    \
+    if (k64) return launch_fprop_batch<BNV, 64>(batch, nb, st);              \
+    return k32 ? launch_fprop_batch<BNV, 32>(batch, nb, st) : launch_fprop_batch<BNV, 16>(batch, nb, st); \
+  }                                                                          \
   if (k64) return launch_fprop<BNV, 64>(p, st);                              \
   return k32 ? launch_fprop<BNV, 32>(p, st) : launch_fprop<BNV, 16>(p, st);
   // widest tile that still gives about one CTA per SM: the decoder's input-gradient GEMMs have M = 256 ... 4096

@@ -270,6 +270,40 @@ def test_convT_phases_in_one_grid_equal_separate_launches(sv, impl, cin, cout, H
     assert rel_rms(from_nhwc(res[1][0].cuda().to(torch.bfloat16)), F.conv_transpose2d(x, w, None, 2, 1)) < 4e-3
 
 
+@pytest.mark.parametrize("cin,cout,c_real,Hin,NB", [(64, 16, 3, 16, 16), (128, 64, 64, 8, 4)])
+def test_convT_phases_in_one_mma_grid_equal_separate_launches(sv, cin, cout, c_real, Hin, NB):
+    """sv_igemm_fprop_batch on the mma.sync kernel (the last decoder layer, 64 -> 3 channels, fp32 output with n_valid):
+    the four output-parity phases in ONE grid (blockIdx.z = phase) equal four separate launches bit for bit"""
+    from shotvae_b200._abi import lib, check, IgemmArgs
+    from shotvae_b200.plan import dgrad_phase_taps, live_taps
+    torch.manual_seed(cin + cout)
+    x = bf(torch.randn(NB, cin, Hin, Hin))
+    w = torch.zeros(cin, cout, 4, 4)
+    w[:, :c_real] = bf(torch.randn(cin, c_real, 4, 4) * 0.05)
+    Ho, A = 2 * Hin, nhwc(x)
+    res = []
+    for batched in (False, True):
+        outf = torch.zeros(NB, Ho, Ho, c_real, dtype=torch.float32, device="cuda")
+        batch = [] if batched else None
+        keep = []
+        for (py, px), taps in dgrad_phase_taps(4, 2, 1).items():
+            taps = live_taps(taps, Hin, Hin, Hin, Hin, 1)
+            Wt = pack(sv, w, cout, cin, taps, c_real, cin, 16, cout * 16, 1, 1)
+            keep.append(Wt)
+            igemm(sv, A, Wt, taps, NB, Hin, Hin, cin, Hin, Hin, cout, outf=outf, out_stride=2, off=(py, px), OHf=Ho, OWf=Ho,
+                  n_valid=c_real, impl=1, batch=batch)
+        if batched:
+            n0 = lib.sv_launch_count()
+            arr = (IgemmArgs * len(batch))(*[b[0] for b in batch])
+            check(lib.sv_igemm_fprop_batch(arr, len(batch), sv.stream()))
+            assert lib.sv_launch_count() - n0 == 1
+        torch.cuda.synchronize()
+        res.append(outf.cpu())
+    assert torch.equal(res[0], res[1])
+    want = F.conv_transpose2d(x, w, None, 2, 1)[:, :c_real]
+    assert rel_rms(res[1].permute(0, 3, 1, 2), want) < 4e-3
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("cin,cout,H,stride,k,NB", [(32, 32, 16, 1, 3, 4), (32, 64, 32, 2, 3, 4), (32, 64, 32, 2, 1, 4), (16, 32, 8, 1, 1, 4)])
 def test_conv_dgrad_phases_match_autograd(sv, impl, cin, cout, H, stride, k, NB):
