@@ -68,6 +68,8 @@ class TrainStep:
         if net.side is None and os.environ.get("SHOTVAE_SIDE", "1") != "0":
             net.side = torch.cuda.Stream(device=net.device)
         self.side2 = torch.cuda.Stream(device=net.device) if net.side is not None else None
+        if net.side is not None and net.side_dec is None and os.environ.get("SHOTVAE_DEC_SIDE", "1") != "0":
+            net.side_dec = torch.cuda.Stream(device=net.device)       # decoder weight gradients beside the decoder's dgrad chain
         dev, B, nd, D = net.device, self.B, net.nd, net.ldc
         self.dev = dev
         f32, i64 = torch.float32, torch.int64
