@@ -68,6 +68,10 @@ class TrainStep:
         if net.side is None and os.environ.get("SHOTVAE_SIDE", "1") != "0":
             net.side = torch.cuda.Stream(device=net.device)
         self.side2 = torch.cuda.Stream(device=net.device) if net.side is not None else None
+        # last-block backward of [P2 | P4] early (see _part0): its own pair of streams
+        self.bwd_split = net.side is not None and (not m2) and os.environ.get("SHOTVAE_BWD_SPLIT", "0") != "0"      # MEASURED: 4.93 vs 4.63 ms/step -- the window is not idle enough, off
+        self.side3 = torch.cuda.Stream(device=net.device) if self.bwd_split else None
+        self.side4 = torch.cuda.Stream(device=net.device) if self.bwd_split else None
         if net.side is not None and net.side_dec is None and os.environ.get("SHOTVAE_DEC_SIDE", "1") != "0":
             net.side_dec = torch.cuda.Stream(device=net.device)       # decoder weight gradients beside the decoder's dgrad chain
         dev, B, nd, D = net.device, self.B, net.nd, net.ldc
@@ -353,6 +357,19 @@ class TrainStep:
                                            ptr(self.m_mu), ptr(self.m_sig), ptr(self.coef[8:]), B, D, nd, ptr(self.terms[8:]),
                                            ptr(g_la2[B:]), ptr(g_mu2[B:]), ptr(g_ls2[B:]), 0, st))
             # (the backward of [P2 | P4] -- heads + encoder only -- runs together with [P1 | P3] in part 1)
+        # The heads + last-resolution-block backward of [P2 | P4] needs only the posterior-matching gradients just computed, not
+        # the decoder chain of [P1 | P3]: it runs NOW, as a G = 2 launch sequence on its own streams, beside that chain (small
+        # grids: 1x1 ... 16x16 decoder layers) instead of after it as half of the G = 4 backward.  Part 1 then runs the same block
+        # for [P1 | P3] only and continues with both pass groups merged from the next block on.
+        self._split_done = False
+        if conc and self.bwd_split:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side3.wait_event(ev)
+            with torch.cuda.stream(self.side3):
+                gfB = net.heads_bwd(Bc, g_mu2, g_ls2, g_la2, side=self.side4)
+                net.encoder_bwd(Bc, gfB, seg=0, side=self.side4)
+            self._split_done = True
         # The decoder forwards of P2 / P4 (kept only for their BatchNorm running statistics) need nothing but [P2 | P4]'s heads.
         # With the two encoder forwards overlapped, the sample -> decoder -> ELBO -> decoder-backward chain of [P1 | P3] is the
         # ONLY chain in flight from here to part 1 (timeline: ~650 us with one kernel at a time, profiles/r02_step_timeline.md):
@@ -368,6 +385,8 @@ class TrainStep:
             self._dead_done = True
         if side is not None:
             main.wait_stream(side)
+        if self._split_done:
+            main.wait_stream(self.side3)
 
     def _dead_decoders(self):
         """decoder forwards of [P2 | P4]: the reference discards these reconstructions (main_shot_vae.py:311,356) but the
@@ -398,10 +417,19 @@ class TrainStep:
         if S is not A and not self._adopted:
             net.adopt_views(S)
             self._adopted = True
-        # heads + encoder backward of ALL pass groups at once (g.mu / g.ls / g.la of the views are slices of S's)
         D, nd = net.ldc, net.nd
-        net.encoder_bwd(S, net.heads_bwd(S, S.t("g.mu", (S.NB, D), torch.float32), S.t("g.ls", (S.NB, D), torch.float32),
-                                         S.t("g.la", (S.NB, nd), torch.float32)), seg=seg)
+        if getattr(self, "_split_done", False):
+            # the last block of [P2 | P4] already ran in part 0: the same block for [P1 | P3], then both merged (the views' buffers
+            # are the two halves of S's, so S continues from the full input-gradient buffer)
+            net.encoder_bwd(A, net.heads_bwd(A, g_mu, g_ls, g_la), seg=0)
+            S._bwd_state = (S.bufs[A._bwd_name], A._bwd_state[1])
+            if seg is None:
+                for i in range(1, len(net.bwd_segments())):
+                    net.encoder_bwd(S, None, seg=i)
+        else:
+            # heads + encoder backward of ALL pass groups at once (g.mu / g.ls / g.la of the views are slices of S's)
+            net.encoder_bwd(S, net.heads_bwd(S, S.t("g.mu", (S.NB, D), torch.float32), S.t("g.ls", (S.NB, D), torch.float32),
+                                             S.t("g.la", (S.NB, nd), torch.float32)), seg=seg)
         if dead and self.side2 is not None:
             main.wait_stream(self.side2)
 

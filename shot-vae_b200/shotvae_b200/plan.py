@@ -635,10 +635,11 @@ class Net:
             hi = lo
         return out
 
-    def encoder_bwd(self, ctx, g_feat, seg=None):
+    def encoder_bwd(self, ctx, g_feat, seg=None, side="net"):
         """g_feat: fp32 [NB, feat].  Accumulates every encoder parameter gradient into the grad arena.
         seg = None: the whole backward; seg = i: only segment i of bwd_segments() (segments must be run in order; the state
-        between them lives in ctx; every segment ends with the side stream joined, so it can be its own CUDA graph)."""
+        between them lives in ctx; every segment ends with the side stream joined, so it can be its own CUDA graph).
+        side: the stream for the weight gradients ("net" = self.side)."""
         topo, NB, G, B = self.topo, ctx.NB, ctx.G, ctx.B
         slope, sslope = topo["slope"], topo["shortcut_slope"]
         segs = self.bwd_segments()
@@ -657,7 +658,7 @@ class Net:
         # kernels next to HBM-bound ones.  Buffers shared between units by shape (g.y1.*, the two g.h flip buffers)
         # are protected by `side_done`: the main stream waits for the previous unit's weight gradients before it
         # overwrites what they read.
-        side = self.side if not self.dry else None
+        side = (self.side if side == "net" else side) if not self.dry else None
         main = torch.cuda.current_stream() if side is not None else None
         side_done = None
 
@@ -734,6 +735,7 @@ class Net:
             g_prev = ctx.t(("g.h.%s" % k) if BWD_DECOUPLE else "g.h.%d.%d.%d" % (Hin, u.cin, flip), (NB, Hin, Hin, u.cin))
             self._bn_bwd(ctx, k + ".bn1", terms, rec["h_in"], addend, g_prev, rows_in, Hin * Hin)
             g_h = g_prev
+            ctx._bwd_name = ("g.h.%s" % k) if BWD_DECOUPLE else "g.h.%d.%d.%d" % (Hin, u.cin, flip)
         if side is not None:
             with torch.cuda.stream(side):
                 self._wgrad_flush()          # the segment's gradients are complete when the side stream is joined
@@ -800,8 +802,8 @@ class Net:
         ctx.feat = feat
         return outs["mu"], outs["ls"], la
 
-    def heads_bwd(self, ctx, g_mu, g_ls, g_la):
-        """returns g_feat fp32 [NB, feat]; accumulates head parameter gradients"""
+    def heads_bwd(self, ctx, g_mu, g_ls, g_la, side="net"):
+        """returns g_feat fp32 [NB, feat]; accumulates head parameter gradients (side: as in encoder_bwd)"""
         NB, Cf = ctx.NB, self.topo["feat"]
         s = _abi.stream()
         g_logits = ctx.t("g.logits", (NB, self.nd), torch.float32)
@@ -814,7 +816,7 @@ class Net:
 
         # the head weight gradients are not needed by the backward chain: side stream (joined at the end of encoder_bwd,
         # which always follows)
-        side = self.side if not self.dry else None
+        side = (self.side if side == "net" else side) if not self.dry else None
         if side is not None:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
