@@ -176,6 +176,10 @@ def test_shot_step_matches_oracle(net, nd, batch, epoch, om, bce, dataset):
         assert abs(got[k] - want[k]) < 1e-3 * max(1.0, abs(want["klc_l"])), (k, terms[k])
     for k in ("disc_post_l", "disc_post_u"):
         assert terms[k]["rel"] < 5e-3, (k, terms[k])
+    # continuous posterior-matching terms: the labelled one is ~1e-10 in FP32 (lambda ~ 1: the mixed pass repeats the labelled
+    # one) and the bf16 network's two passes differ by ~6e-4 there -> absolute 2e-3 plus 5 % (measured: <= 1e-3 and <= 1.2 %)
+    for k in ("cont_post_l", "cont_post_u"):
+        assert abs(got[k] - want[k]) <= 2e-3 + 5e-2 * abs(want[k]), (k, terms[k])
     errs = grad_errors(grads, wgrads)
     _report("grad_rel_l2_" + tag, errs)
     # same-precision control: the oracle under autocast(bfloat16) against the FP32 oracle
