@@ -48,6 +48,7 @@ class GradReducer:
                 self.segments.append("enc%d" % i)
             assert sum(e - s for s, e in (self.buckets[k] for k in self.segments)) == split, "encoder segments do not tile the encoder range"
         self.bytes_per_step = net.n_params * 4
+        self.events = {}             # bucket name -> event recorded behind its all-reduce (wait_bucket)
         # SMs left to NCCL while a bucket is in flight.  The tcgen05 conv / weight-gradient kernels are persistent grids with
         # statically strided tiles, one CTA per SM: if a collective holds k SMs when such a grid starts, its last k CTAs form a
         # second wave and the kernel takes twice as long (MEASURED at 8 GPUs: 24 NVLS channels, 4.81 -> 5.04 ms/step).  With
@@ -89,6 +90,15 @@ class GradReducer:
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             dist.all_reduce(self.net.grads[s:e], op=dist.ReduceOp.SUM, group=self.group)
+            ev = self.events.get(name)
+            if ev is None:
+                ev = self.events[name] = torch.cuda.Event()
+            ev.record(self.stream)
+
+    def wait_bucket(self, name):
+        """the compute stream waits for this bucket's all-reduce (and, the reducer stream being ordered, every earlier one)"""
+        if self.cuda and name in self.events:
+            torch.cuda.current_stream().wait_event(self.events[name])
 
     def wait_all(self):
         if self.cuda:

@@ -242,6 +242,10 @@ class TrainStep:
                 self._part0()
             elif part == 2:
                 self._part2()
+            elif part == "2a":
+                self._part2(rng=(self._sgd_split, self.net.n_params), running=False)
+            elif part == "2b":
+                self._part2(rng=(0, self._sgd_split), running=True)
             else:
                 if limit:
                     lib.sv_set_cta_limit(limit)
@@ -256,7 +260,15 @@ class TrainStep:
         segs = self.reducer.segments if self.reducer is not None else []
         if len(segs) < 2:
             return [((0,), "decoder"), ((1,), "encoder"), ((2,), None)]
-        return [((0,), "decoder")] + [(((1, i),), name) for i, name in enumerate(segs)] + [((2,), None)]
+        plan = [((0,), "decoder")] + [(((1, i),), name) for i, name in enumerate(segs)]
+        # The optimizer in two launches: every range whose all-reduce is already behind the compute stream (all buckets but the
+        # last, small, fully exposed one) is updated WHILE that last all-reduce is in flight, the rest after it.  The split
+        # point is rounded up to the kernel's 16-byte granularity; `wait` names the bucket the part waits for.
+        lo_last, hi_last = self.reducer.buckets[segs[-1]]
+        self._sgd_split = min(self.net.n_params, (hi_last + 3) // 4 * 4) if lo_last == 0 else 0
+        if self._sgd_split and os.environ.get("SHOTVAE_DDP_SGD_SPLIT", "1") != "0":
+            return plan + [(("2a",), None, segs[-2]), (("2b",), None, None)]
+        return plan + [((2,), None)]
 
     def _part0(self):
         net, B, st = self.net, self.B, _abi.stream()
@@ -433,10 +445,14 @@ class TrainStep:
         if dead and self.side2 is not None:
             main.wait_stream(self.side2)
 
-    def _part2(self):
+    def _part2(self, rng=None, running=True):
         net, A, Bc, st = self.net, self.ctxA, self.ctxB, _abi.stream()
-        # ---- optimizer + BatchNorm running statistics
-        check(lib.sv_sgd_step(ptr(net.params), ptr(net.grads), ptr(net.momentum), ptr(self.sgd_hyper), net.n_params, st))
+        # ---- optimizer (rng: a [lo, hi) slice of the flat arena) + BatchNorm running statistics
+        lo, hi = rng if rng is not None else (0, net.n_params)
+        if hi > lo:
+            check(lib.sv_sgd_step(ptr(net.params[lo:hi]), ptr(net.grads[lo:hi]), ptr(net.momentum[lo:hi]), ptr(self.sgd_hyper), hi - lo, st))
+        if not running:
+            return
         if self.m2:
             net.bn_running_update([(A, 0), (A, 1)])
         else:
@@ -447,9 +463,10 @@ class TrainStep:
         if self.reducer is None:
             self._sequence()
             return
-        for parts, bucket in self._ddp_plan():
+        for ent in self._ddp_plan():
+            parts, bucket = ent[0], ent[1]
             if bucket is None:
-                self.reducer.wait_all()
+                self._ddp_wait(ent)
             self._sequence(parts)
             if bucket is not None:
                 self.reducer.bucket_ready(bucket)      # overlaps with the next part of the backward
@@ -471,7 +488,7 @@ class TrainStep:
                     self._run_parts_eager()
                 graphs = [g]
             else:
-                groups = [(0, 1, 2)] if self.reducer is None else [parts for parts, _ in self._ddp_plan()]
+                groups = [(0, 1, 2)] if self.reducer is None else [ent[0] for ent in self._ddp_plan()]
                 graphs = []
                 for parts in groups:
                     g = torch.cuda.CUDAGraph()
@@ -496,12 +513,20 @@ class TrainStep:
         if self.reducer is None or len(self.graph) == 1:
             self.graph[0].replay()
             return
-        for g, (_, bucket) in zip(self.graph, self._ddp_plan()):
+        for g, ent in zip(self.graph, self._ddp_plan()):
+            bucket = ent[1]
             if bucket is None:
-                self.reducer.wait_all()
+                self._ddp_wait(ent)
             g.replay()
             if bucket is not None:
                 self.reducer.bucket_ready(bucket)
+
+    def _ddp_wait(self, ent):
+        """before an optimizer part of the data-parallel plan: wait for the bucket it names, or for all of them"""
+        if len(ent) > 2 and ent[2] is not None:
+            self.reducer.wait_bucket(ent[2])
+        else:
+            self.reducer.wait_all()
 
     def load_inputs(self, image_l, label_l, image_u, label_u, draws="auto"):
         """host -> device copy of one (labelled, unlabelled) batch pair through pinned staging buffers,
