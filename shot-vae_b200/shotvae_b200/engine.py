@@ -68,6 +68,11 @@ class TrainStep:
         if net.side is None and os.environ.get("SHOTVAE_SIDE", "1") != "0":
             net.side = torch.cuda.Stream(device=net.device)
         self.side2 = torch.cuda.Stream(device=net.device) if net.side is not None else None
+        # The forward of [P1 | P3] and its sample -> decoder -> ELBO -> decoder-backward chain (the critical chain between the
+        # encoder forwards and the encoder backward) run on a HIGH-priority stream: stream priorities survive CUDA-graph capture
+        # (kernel-node priority), so its kernels get SMs before the dead decoder forwards and the decoder weight gradients that
+        # run beside it.  MEASURED: C2 4.632 -> 4.589 ms/step (A/B x 3), C4 / C5 unchanged.  SHOTVAE_PRIO=0: default priority.
+        self.side_a = torch.cuda.Stream(device=net.device, priority=-1) if (net.side is not None and os.environ.get("SHOTVAE_PRIO", "1") != "0") else None
         # last-block backward of [P2 | P4] early (see _part0): its own pair of streams
         self.bwd_split = net.side is not None and (not m2) and os.environ.get("SHOTVAE_BWD_SPLIT", "0") != "0"      # MEASURED: 4.93 vs 4.63 ms/step -- the window is not idle enough, off
         self.side3 = torch.cuda.Stream(device=net.device) if self.bwd_split else None
@@ -297,17 +302,31 @@ class TrainStep:
                                         ptr(xB[B:]), cp, None, None, None, s2))
                 featB = net.encoder_fwd(Bc, xB)
                 mu2, ls2, la2 = net.heads_fwd(Bc, featB)
-        # ---- forward of [P1 | P3]
-        xA = A.t("x_img", (2 * B, 32, 32, cp))
-        check(net.fn("sv_pack_image")(ptr(self.img_l), ptr(xA[:B]), B, ch, 32 * 32, cp, st))
-        check(net.fn("sv_pack_image")(ptr(self.img_u), ptr(xA[B:]), B, ch, 32 * 32, cp, st))
-        feat = net.encoder_fwd(A, xA)
-        mu, ls, la = net.heads_fwd(A, feat)
+        # ---- forward of [P1 | P3].  With SHOTVAE_PRIO=1 and the two forwards overlapped it runs on the HIGH-priority stream that
+        # also carries the decoder chain: [P1 | P3]'s forward then finishes first and its decoder chain -- the critical path to
+        # the encoder backward -- overlaps the rest of [P2 | P4]'s forward instead of starting when both forwards end.
+        hp = conc and self.side_a is not None
+        evA = None
+        if hp:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.side_a.wait_event(ev)
+        with (torch.cuda.stream(self.side_a) if hp else contextlib.nullcontext()):
+            xA = A.t("x_img", (2 * B, 32, 32, cp))
+            check(net.fn("sv_pack_image")(ptr(self.img_l), ptr(xA[:B]), B, ch, 32 * 32, cp, _abi.stream()))
+            check(net.fn("sv_pack_image")(ptr(self.img_u), ptr(xA[B:]), B, ch, 32 * 32, cp, _abi.stream()))
+            feat = net.encoder_fwd(A, xA)
+            mu, ls, la = net.heads_fwd(A, feat)
+            if hp:
+                evA = torch.cuda.Event()
+                evA.record(self.side_a)
         # From here two independent chains run until part 1: (a) sample -> decoder forward -> ELBO terms -> decoder
         # backward of [P1 | P3], and (b) mixup -> encoder forward of [P2 | P4] -> posterior-matching terms.  (a) goes to
         # the side stream: its many small launches (1x1 ... 8x8 decoder layers, loss reductions) fill the gaps of (b)'s
         # large persistent convolutions.
         side = net.side if not self.m2 else None
+        if side is not None and self.side_a is not None:
+            side = self.side_a          # (experiment: the critical decoder chain on a high-priority stream, see __init__)
         main = torch.cuda.current_stream()
 
         def fork():
@@ -333,6 +352,8 @@ class TrainStep:
             self._g = (g_mu, g_ls, g_la)
         if conc:
             # the mixing targets of the posterior terms need [P1 | P3]'s latents; then join the second forward
+            if evA is not None:
+                main.wait_event(evA)
             check(lib.sv_mixup_lerp(None, ptr(mu[:B]), ptr(ls[:B]), ptr(la[:B]), ptr(self.idx_l), ptr(self.lam), B, ch, 32 * 32, D, nd,
                                     None, None, 0, ptr(self.s_mu), ptr(self.s_sig), ptr(self.s_alpha), st))
             check(lib.sv_mixup_lerp(None, ptr(mu[B:]), ptr(ls[B:]), ptr(la[B:]), ptr(self.idx_u), ptr(self.lam[2:]), B, ch, 32 * 32, D, nd,
