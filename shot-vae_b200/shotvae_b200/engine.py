@@ -405,7 +405,7 @@ class TrainStep:
             self._split_done = True
         # The decoder forwards of P2 / P4 (kept only for their BatchNorm running statistics) need nothing but [P2 | P4]'s heads.
         # With the two encoder forwards overlapped, the sample -> decoder -> ELBO -> decoder-backward chain of [P1 | P3] is the
-        # ONLY chain in flight from here to part 1 (timeline: ~650 us with one kernel at a time, profiles/r02_step_timeline.md):
+        # ONLY chain in flight from here to part 1 (timeline: ~650 us with one kernel at a time, profiles/r02_timeline_c2.txt, profiles/r02_kernel_findings.md section 8):
         # the dead forwards fill it instead of competing with the encoder backward.  SHOTVAE_DEAD_EARLY=0: beside part 1.
         self._dead_done = False
         if conc and not self.skip_dead_decoders and os.environ.get("SHOTVAE_DEAD_EARLY", "1") != "0":
